@@ -1,0 +1,184 @@
+/* include/pkwhir.h — C-ABI of libpkwhir.so: the B200 (sm_100a) WHIR hot path of `noir-r1cs prove`.
+ *
+ * The reference (worldfnd/provekit, Rust) has no FFI today; its plug-in seams for this path are Rust
+ * traits / fn types.  Each entry point below names the reference interface it replaces.
+ * A Rust host binds these with a `extern "C"` block (INTEGRATION.md shows the shim) and keeps its
+ * CLI, witness solving, .nps/.np files and the Fiat-Shamir ProverState.
+ *
+ * Conventions
+ *   - Field elements cross the ABI in arkworks' in-memory form: 4 x u64 little-endian limbs,
+ *     Montgomery form (R = 2^256), i.e. `FieldElement = ark_ff::Fp<MontBackend<BN254Config,4>,4>`
+ *     (provekit/common/src/lib.rs:19) can be passed by pointer without conversion.  Parameters
+ *     documented as "canonical" are plain little-endian 256-bit integers (the hash-input / wire form,
+ *     provekit/common/src/skyscraper/whir.rs:21-24).
+ *   - Every function returns PK_OK (0) or a negative pk_status; pk_last_error(ctx) gives text.
+ *     Where the reference panics (assert!/expect, e.g. provekit/common/src/utils/sumcheck.rs:21-24,
+ *     provekit/prover/src/whir_r1cs.rs:206) this ABI returns PK_ERR_INVALID_ARG instead of unwinding.
+ *   - One pk_ctx per host thread (owns one CUDA stream); calls are synchronous from the caller's
+ *     view unless documented otherwise.  No CPU fallback exists: with no usable CUDA device
+ *     pk_ctx_create fails with PK_ERR_NO_DEVICE.
+ *   - pk_buf is a device-resident array of field elements; "host" pointers are ordinary memory.
+ */
+#ifndef PKWHIR_H
+#define PKWHIR_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    PK_OK = 0,
+    PK_ERR_INVALID_ARG = -1,   /* the reference's assert!/panic conditions */
+    PK_ERR_NO_DEVICE = -2,
+    PK_ERR_CUDA = -3,
+    PK_ERR_OOM = -4,
+    PK_ERR_INTERNAL = -5,
+    PK_ERR_EMPTY_INPUT = -6    /* ark Error::IncorrectInputLength(0), skyscraper/whir.rs:47 */
+} pk_status;
+
+typedef struct pk_ctx pk_ctx;
+typedef struct pk_buf pk_buf;
+typedef struct pk_commitment pk_commitment;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int pk_ctx_create(int device, pk_ctx **out);
+void pk_ctx_destroy(pk_ctx *ctx);
+const char *pk_last_error(const pk_ctx *ctx);
+const char *pk_version(void);
+/* number of CUDA kernels this ctx has launched so far (bench.py's gpu_launches) */
+uint64_t pk_launch_count(const pk_ctx *ctx);
+/* raw cudaStream_t of the ctx (for CUDA-event timing by the caller) */
+void *pk_ctx_stream(pk_ctx *ctx);
+int pk_ctx_sync(pk_ctx *ctx);
+
+/* ---- device buffers of field elements -------------------------------------------------------- */
+int pk_buf_alloc(pk_ctx *ctx, size_t n_elems, pk_buf **out);
+void pk_buf_free(pk_ctx *ctx, pk_buf *buf);
+size_t pk_buf_len(const pk_buf *buf);
+void *pk_buf_device_ptr(pk_buf *buf);
+int pk_buf_upload(pk_ctx *ctx, pk_buf *dst, size_t dst_off, const uint64_t *host, size_t n_elems);
+int pk_buf_download(pk_ctx *ctx, const pk_buf *src, size_t src_off, uint64_t *host, size_t n_elems);
+int pk_buf_copy(pk_ctx *ctx, pk_buf *dst, size_t dst_off, const pk_buf *src, size_t src_off, size_t n_elems);
+int pk_buf_zero(pk_ctx *ctx, pk_buf *dst, size_t off, size_t n_elems);
+
+/* ---- seam: skyscraper::CompressManyFn ---------------------------------------------------------
+ * `pub type CompressManyFn = fn(&[u8], &mut [u8])` (skyscraper/core/src/lib.rs:26; contract
+ * generic.rs:14-37): n messages of 64 B (two canonical LE 256-bit integers, any value < 2^256)
+ * -> n hashes of 32 B (canonical, < p).  Host buffers. */
+int pk_skyscraper_compress_many(pk_ctx *ctx, const uint8_t *messages, uint8_t *hashes, size_t n);
+/* same on device-resident data (messages: 2n elems, hashes: n elems, canonical form) */
+int pk_skyscraper_compress_many_dev(pk_ctx *ctx, const pk_buf *messages, pk_buf *hashes, size_t n);
+
+/* ---- seam: PowStrategy (provekit/common/src/skyscraper/pow.rs:14-30 -> skyscraper::pow::solve,
+ * skyscraper/core/src/pow.rs:33-41): smallest nonce with compress(challenge,[nonce,0,0,0]) <
+ * threshold(bits + 0.01).  challenge: canonical 4 x u64.  bits must be in [0, 60). */
+int pk_pow_solve(pk_ctx *ctx, const uint64_t challenge[4], double bits, uint64_t *nonce);
+
+/* ---- seam: EvaluationsList::to_coeffs / CoefficientList -> EvaluationsList [whir] -------------
+ * call sites provekit/prover/src/whir_r1cs.rs:195,198.  In place on 2^log_n elements. */
+int pk_evals_to_coeffs(pk_ctx *ctx, pk_buf *buf, int log_n);
+int pk_coeffs_to_evals(pk_ctx *ctx, pk_buf *buf, int log_n);
+
+/* ---- seam: CommitmentWriter::commit_batch [whir], call site whir_r1cs.rs:200-206 -------------
+ * RS-encodes `batch` coefficient vectors of 2^log_n on the domain 2^(log_n+log_inv_rate)
+ * ("prover helps" leaves of 2^fold per polynomial, stacked per leaf), builds the Skyscraper Merkle
+ * tree (SkyscraperMerkleConfig, provekit/common/src/skyscraper/whir.rs:27-86) and returns the root
+ * (Montgomery form, = MerkleConfig::InnerDigest).  The commitment keeps leaves + tree on device. */
+int pk_commit_batch(pk_ctx *ctx, const pk_buf *const *coeffs, int batch, int log_n, int log_inv_rate,
+                    int fold, pk_commitment **out, uint64_t root_out[4]);
+void pk_commit_free(pk_ctx *ctx, pk_commitment *c);
+size_t pk_commit_num_leaves(const pk_commitment *c);
+size_t pk_commit_leaf_width(const pk_commitment *c);
+/* the two stages of pk_commit_batch, exposed for measurement: codeword only / tree only */
+int pk_rs_encode(pk_ctx *ctx, const pk_buf *coeffs, int log_n, int log_inv_rate, int fold, pk_buf *leaves,
+                 size_t leaf_stride, size_t col_offset);
+/* nodes: 2L elements, heap order (nodes[1] = root, leaf digests at [L,2L)), canonical digests */
+int pk_merkle_build(pk_ctx *ctx, const pk_buf *leaves, size_t num_leaves, size_t leaf_width, pk_buf *nodes);
+
+/* ---- seam: MerkleTree::generate_multi_proof + STIR answers [whir/ark-crypto-primitives] -------
+ * sorted_idx: strictly increasing leaf indexes.  leaves_out: n_idx * leaf_width elements (Montgomery).
+ * ark MultiPath pieces (canonical 32-byte digests): sibling_out[n_idx*4]; prefix_len_out[n_idx];
+ * suffix_out holds the concatenated suffixes (root->leaf order), suffix_len_out[n_idx] their lengths;
+ * suffix_cap = capacity of suffix_out in digests (n_idx * depth always suffices). */
+int pk_commit_open(pk_ctx *ctx, const pk_commitment *c, const uint64_t *sorted_idx, size_t n_idx,
+                   uint64_t *leaves_out, uint64_t *sibling_out, uint64_t *prefix_len_out,
+                   uint64_t *suffix_out, uint64_t *suffix_len_out, size_t suffix_cap);
+
+/* ---- univariate / multilinear helpers used by commit_batch and Prover::prove [whir] ---------- */
+/* OOD answer: coefficient vector evaluated at (z^(2^(n-1)),..,z^2,z) = Horner at z */
+int pk_eval_univariate(pk_ctx *ctx, const pk_buf *coeffs, size_t n, const uint64_t z[4], uint64_t out[4]);
+/* y[i] += a * x[i]  (batching p0 + b*p1; linear-weight accumulation) */
+int pk_axpy(pk_ctx *ctx, pk_buf *y, const pk_buf *x, const uint64_t a[4], size_t n);
+/* Weights::weighted_sum: <a, b> over n elements (call site whir_r1cs.rs:398-399) */
+int pk_dot(pk_ctx *ctx, const pk_buf *a, const pk_buf *b, size_t n, uint64_t out[4]);
+/* eval_eq (provekit/common/src/utils/sumcheck.rs:145-171): out[idx] += scalar * eq(point, idx),
+ * point[0] <-> most significant index bit; n variables */
+int pk_eval_eq(pk_ctx *ctx, const uint64_t *point, int n, const uint64_t scalar[4], pk_buf *out);
+/* several points at once: out[idx] += sum_k scalars[k] * eq(points[k], idx)  (STIR/OOD constraints) */
+int pk_eval_eq_batch(pk_ctx *ctx, const uint64_t *points, size_t k, int n, const uint64_t *scalars, pk_buf *out);
+/* Weights::linear(w).compute(point): sum_idx evals[idx] * eq(point, idx) */
+int pk_mle_eval(pk_ctx *ctx, const pk_buf *evals, int log_n, const uint64_t *point, uint64_t out[4]);
+/* CoefficientList::fold: 2^k consecutive coefficients -> 1; r[j] binds bit j of the in-block index */
+int pk_fold_coeffs(pk_ctx *ctx, const pk_buf *coeffs, int log_n, const uint64_t *r, int k, pk_buf *out);
+
+/* ---- seam: sumcheck_fold_map_reduce (provekit/common/src/utils/sumcheck.rs:16-39) -------------
+ * with the map of run_zk_sumcheck_prover (provekit/prover/src/whir_r1cs.rs:284-291).  The four
+ * arrays hold 2^log_n elements; if fold != NULL they are first folded in place by
+ * x[i] += fold*(x[i+len/2]-x[i]) and the caller treats them as 2^(log_n-1) long afterwards
+ * (the reference truncates, whir_r1cs.rs:293-298).  out3 = [f(0), f(-1), f(inf)] (Montgomery).
+ * Asserts of the reference (power of two, >= 2, >= 4 when folding) -> PK_ERR_INVALID_ARG. */
+int pk_zk_sumcheck_round(pk_ctx *ctx, pk_buf *a, pk_buf *b, pk_buf *c, pk_buf *eq, int log_n,
+                         const uint64_t *fold_or_null, uint64_t out3[12]);
+
+/* ---- seam: whir SumcheckSingle::compute_sumcheck_polynomial + compress ------------------------
+ * LSB pairing (elements 2i, 2i+1).  If fold != NULL: p_out[i] = p_in[2i] + fold*(p_in[2i+1]-p_in[2i])
+ * (same for w) over 2^(log_n-1) outputs, and the round polynomial is computed on the folded arrays;
+ * otherwise it is computed on p_in/w_in directly (p_out/w_out may be NULL).  out3 = [h(0),h(1),h(2)]. */
+int pk_whir_sumcheck_round(pk_ctx *ctx, const pk_buf *p_in, const pk_buf *w_in, pk_buf *p_out, pk_buf *w_out,
+                           int log_n, const uint64_t *fold_or_null, uint64_t out3[12]);
+
+/* ---- seam: WhirR1CSProver::prove (provekit/prover/src/whir_r1cs.rs:42-100) --------------------
+ * The whole hot path driven by this library's own host-side Fiat-Shamir transcript
+ * (provekit_b200/csrc/host/).  R1CS in the reference's interned-CSR form
+ * (provekit/common/src/sparse_matrix.rs:19-26, interner.rs). */
+typedef struct {
+    uint64_t num_rows, num_cols, nnz;
+    const uint64_t *row_start; /* num_rows offsets into col/val */
+    const uint32_t *col;
+    const uint32_t *val;       /* indices into pk_r1cs.interned */
+} pk_csr;
+typedef struct {
+    uint64_t num_constraints, num_witnesses, num_interned;
+    const uint64_t *interned;  /* Montgomery field elements */
+    pk_csr a, b, c;
+} pk_r1cs;
+/* The reference draws these from thread_rng (zk_utils.rs:13-22, whir_r1cs.rs:211-225); the host
+ * supplies them so that proofs are reproducible. */
+typedef struct {
+    const uint64_t *mask_w;  /* 2^(m-1) */
+    const uint64_t *g_w;     /* 2^m */
+    const uint64_t *blind;   /* 4*m_0 cubic coefficients */
+    const uint64_t *mask_h;  /* 2^(mh-1) */
+    const uint64_t *g_h;     /* 2^mh */
+} pk_rand;
+typedef struct pk_prover pk_prover;
+/* uploads the R1CS once (scheme-time work, like reading the .nps) */
+int pk_prover_create(pk_ctx *ctx, const pk_r1cs *r1cs, pk_prover **out);
+void pk_prover_destroy(pk_prover *p);
+/* returns the spongefish NARG string (= WhirR1CSProof.transcript); *out is malloc'd, free with pk_free */
+int pk_prove(pk_prover *p, const uint64_t *witness, const pk_rand *rnd, uint8_t **out, size_t *out_len);
+void pk_free(void *p);
+/* seconds spent per stage in the last pk_prove: [commit_ntt, commit_merkle, zk_sumcheck, whir_sumcheck,
+ * pow, open, spmv_weights, other, total] */
+void pk_prover_timings(const pk_prover *p, double out[9]);
+
+/* ---- measurement helper (no reference counterpart): `iters` dependent Montgomery multiplications
+ * in two chains per thread on n_threads threads; *ms_out = device time.  Gives the modmul/s ceiling
+ * of the integer pipe that DESIGN.md quotes next to the HBM roofline. */
+int pk_modmul_bench(pk_ctx *ctx, size_t n_threads, int iters, float *ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,214 @@
+"""Host-side mirror (Python, for the test/bench harness) of the reference's operator interface on the
+WHIR hot path.  Every call goes through the C-ABI of libpkwhir.so; nothing here computes on the CPU.
+
+Names follow the reference:
+  compress_many            skyscraper::CompressManyFn                     skyscraper/core/src/lib.rs:26
+  pow_solve                SkyscraperPoW::solve                           provekit/common/src/skyscraper/pow.rs:27-29
+  evals_to_coeffs          EvaluationsList::to_coeffs  [whir]             provekit/prover/src/whir_r1cs.rs:195
+  commit_batch             CommitmentWriter::commit_batch [whir]          provekit/prover/src/whir_r1cs.rs:200-206
+  sumcheck_fold_map_reduce provekit_common::utils::sumcheck::...          provekit/common/src/utils/sumcheck.rs:16-39
+  whir_sumcheck_round      SumcheckSingle::compute_sumcheck_polynomial [whir]
+  prove                    WhirR1CSProver::prove                          provekit/prover/src/whir_r1cs.rs:42-100
+Field elements are numpy uint64 arrays of shape (n, 4): arkworks' Montgomery limbs.
+"""
+import ctypes
+from ctypes import byref, c_double, c_float, c_size_t, c_uint64, c_void_p
+
+import numpy as np
+
+from . import _abi
+from ._abi import PkError
+
+
+def _p(a):
+    return a.ctypes.data_as(c_void_p) if a is not None else None
+
+
+def _fe(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a.reshape(-1, 4)
+
+
+class Buffer:
+    def __init__(self, ctx: "Context", n: int):
+        self.ctx, self.n = ctx, n
+        h = c_void_p()
+        ctx._chk(ctx.L.pk_buf_alloc(ctx.h, n, byref(h)))
+        self.h = h
+
+    def upload(self, arr, off: int = 0) -> "Buffer":
+        arr = _fe(arr)
+        self.ctx._chk(self.ctx.L.pk_buf_upload(self.ctx.h, self.h, off, _p(arr), len(arr)))
+        return self
+
+    def download(self, n: int = None, off: int = 0) -> np.ndarray:
+        n = self.n - off if n is None else n
+        out = np.empty((n, 4), np.uint64)
+        self.ctx._chk(self.ctx.L.pk_buf_download(self.ctx.h, self.h, off, _p(out), n))
+        return out
+
+    def zero(self, off=0, n=None):
+        self.ctx._chk(self.ctx.L.pk_buf_zero(self.ctx.h, self.h, off, self.n - off if n is None else n))
+        return self
+
+    def free(self):
+        if self.h:
+            self.ctx.L.pk_buf_free(self.ctx.h, self.h)
+            self.h = None
+
+    @property
+    def device_ptr(self) -> int:
+        return self.ctx.L.pk_buf_device_ptr(self.h)
+
+
+class Commitment:
+    """Witness{merkle_tree, merkle_leaves} of whir's commit_batch, resident on the device."""
+
+    def __init__(self, ctx, h, root):
+        self.ctx, self.h, self.root = ctx, h, root
+        self.num_leaves = ctx.L.pk_commit_num_leaves(h)
+        self.leaf_width = ctx.L.pk_commit_leaf_width(h)
+        self.depth = self.num_leaves.bit_length() - 1
+
+    def open(self, sorted_indexes):
+        """STIR answers + ark MultiPath pieces for strictly increasing leaf indexes.
+        Returns (leaves (n,w,4) Montgomery, siblings (n,4) canonical, prefix_lens, suffixes list of (k,4))."""
+        idx = np.ascontiguousarray(sorted_indexes, dtype=np.uint64)
+        n = len(idx)
+        leaves = np.empty((n * self.leaf_width, 4), np.uint64)
+        sib = np.empty((n, 4), np.uint64)
+        pre = np.empty(n, np.uint64)
+        slen = np.empty(n, np.uint64)
+        cap = n * max(self.depth, 1)
+        suf = np.empty((cap, 4), np.uint64)
+        self.ctx._chk(self.ctx.L.pk_commit_open(self.ctx.h, self.h, _p(idx), n, _p(leaves), _p(sib), _p(pre), _p(suf),
+                                               _p(slen), cap))
+        sufs, pos = [], 0
+        for k in slen:
+            sufs.append(suf[pos:pos + int(k)].copy())
+            pos += int(k)
+        return leaves.reshape(n, self.leaf_width, 4), sib, pre, sufs
+
+    def free(self):
+        if self.h:
+            self.ctx.L.pk_commit_free(self.ctx.h, self.h)
+            self.h = None
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self.L = _abi.lib()
+        h = c_void_p()
+        rc = self.L.pk_ctx_create(device, byref(h))
+        if rc != 0:
+            raise PkError(rc, "pk_ctx_create failed (no usable CUDA device? this package has no CPU fallback)")
+        self.h = h
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise PkError(rc, self.L.pk_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.L.pk_ctx_destroy(self.h)
+            self.h = None
+
+    @property
+    def launches(self) -> int:
+        return self.L.pk_launch_count(self.h)
+
+    @property
+    def stream(self) -> int:
+        return self.L.pk_ctx_stream(self.h)
+
+    def sync(self):
+        self._chk(self.L.pk_ctx_sync(self.h))
+
+    def buffer(self, n: int) -> Buffer:
+        return Buffer(self, n)
+
+    def upload(self, arr) -> Buffer:
+        arr = _fe(arr)
+        return Buffer(self, len(arr)).upload(arr)
+
+    # ---- seams -------------------------------------------------------------------------------
+    def compress_many(self, messages: bytes) -> bytes:
+        if len(messages) % 64:
+            raise ValueError("Message length not a multiple of 64")  # generic.rs:19
+        n = len(messages) // 64
+        src = np.frombuffer(messages, dtype=np.uint8)
+        out = np.empty(n * 32, np.uint8)
+        self._chk(self.L.pk_skyscraper_compress_many(self.h, _p(src), _p(out), n))
+        return out.tobytes()
+
+    def pow_solve(self, challenge, bits: float) -> int:
+        ch = np.ascontiguousarray(challenge, dtype=np.uint64)
+        nonce = c_uint64()
+        self._chk(self.L.pk_pow_solve(self.h, _p(ch), c_double(bits), byref(nonce)))
+        return nonce.value
+
+    def evals_to_coeffs(self, buf: Buffer, log_n: int):
+        self._chk(self.L.pk_evals_to_coeffs(self.h, buf.h, log_n))
+
+    def coeffs_to_evals(self, buf: Buffer, log_n: int):
+        self._chk(self.L.pk_coeffs_to_evals(self.h, buf.h, log_n))
+
+    def commit_batch(self, polys, log_n: int, log_inv_rate: int = 1, fold: int = 4) -> Commitment:
+        arr = (c_void_p * len(polys))(*[p.h for p in polys])
+        h = c_void_p()
+        root = np.empty(4, np.uint64)
+        self._chk(self.L.pk_commit_batch(self.h, arr, len(polys), log_n, log_inv_rate, fold, byref(h), _p(root)))
+        return Commitment(self, h, root)
+
+    def rs_encode(self, coeffs: Buffer, log_n, log_inv_rate, leaves: Buffer, leaf_stride=16, col_offset=0, fold=4):
+        self._chk(self.L.pk_rs_encode(self.h, coeffs.h, log_n, log_inv_rate, fold, leaves.h, leaf_stride, col_offset))
+
+    def merkle_build(self, leaves: Buffer, num_leaves: int, leaf_width: int, nodes: Buffer):
+        self._chk(self.L.pk_merkle_build(self.h, leaves.h, num_leaves, leaf_width, nodes.h))
+
+    def eval_univariate(self, coeffs: Buffer, n: int, z) -> np.ndarray:
+        out = np.empty(4, np.uint64)
+        self._chk(self.L.pk_eval_univariate(self.h, coeffs.h, n, _p(_fe(z)), _p(out)))
+        return out
+
+    def axpy(self, y: Buffer, x: Buffer, a, n: int):
+        self._chk(self.L.pk_axpy(self.h, y.h, x.h, _p(_fe(a)), n))
+
+    def dot(self, a: Buffer, b: Buffer, n: int) -> np.ndarray:
+        out = np.empty(4, np.uint64)
+        self._chk(self.L.pk_dot(self.h, a.h, b.h, n, _p(out)))
+        return out
+
+    def eval_eq(self, points, scalars, n: int, out: Buffer):
+        pts, sc = _fe(points), _fe(scalars)
+        self._chk(self.L.pk_eval_eq_batch(self.h, _p(pts), len(sc), n, _p(sc), out.h))
+
+    def mle_eval(self, evals: Buffer, log_n: int, point) -> np.ndarray:
+        out = np.empty(4, np.uint64)
+        self._chk(self.L.pk_mle_eval(self.h, evals.h, log_n, _p(_fe(point)), _p(out)))
+        return out
+
+    def fold_coeffs(self, coeffs: Buffer, log_n: int, r, out: Buffer):
+        r = _fe(r)
+        self._chk(self.L.pk_fold_coeffs(self.h, coeffs.h, log_n, _p(r), len(r), out.h))
+
+    def sumcheck_fold_map_reduce(self, a: Buffer, b: Buffer, c: Buffer, eq: Buffer, log_n: int, fold=None) -> np.ndarray:
+        """[f(0), f(-1), f(inf)] of the zk-sumcheck round; folds the four arrays in place first when
+        `fold` is given (log_n = length before folding)."""
+        out = np.empty((3, 4), np.uint64)
+        f = _fe(fold) if fold is not None else None
+        self._chk(self.L.pk_zk_sumcheck_round(self.h, a.h, b.h, c.h, eq.h, log_n, _p(f), _p(out)))
+        return out
+
+    def whir_sumcheck_round(self, p_in: Buffer, w_in: Buffer, log_n: int, fold=None, p_out: Buffer = None,
+                            w_out: Buffer = None) -> np.ndarray:
+        out = np.empty((3, 4), np.uint64)
+        f = _fe(fold) if fold is not None else None
+        self._chk(self.L.pk_whir_sumcheck_round(self.h, p_in.h, w_in.h, p_out.h if p_out else None,
+                                                w_out.h if w_out else None, log_n, _p(f), _p(out)))
+        return out
+
+    def modmul_bench(self, n_threads: int, iters: int) -> float:
+        ms = c_float()
+        self._chk(self.L.pk_modmul_bench(self.h, n_threads, iters, byref(ms)))
+        return ms.value

@@ -1,0 +1,664 @@
+// provekit_b200/csrc/kernels.cu — hand-written sm_100a kernels for the WHIR hot path.
+// See kernels.cuh for the launcher contracts and DESIGN.md for layouts / rooflines.
+#include "kernels.cuh"
+
+#include "fr.cuh"
+#include "skyscraper.cuh"
+
+namespace pk {
+
+static __device__ __forceinline__ fr arg_fr(const fr_arg& a) {
+    fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = a.v[i];
+    return r;
+}
+
+static inline int grid_for(size_t work, int threads, int max_blocks) {
+    size_t b = (work + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > (size_t)max_blocks) b = max_blocks;
+    return (int)b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reductions of field sums
+// ------------------------------------------------------------------------------------------------
+static __device__ __forceinline__ fr fr_shfl_down(const fr& x, int delta) {
+    fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_down_sync(0xffffffffu, x.v[i], delta);
+    return r;
+}
+
+// every thread contributes acc[NS]; thread 0 of the block writes the block sum to out[NS]
+template <int NS>
+static __device__ __forceinline__ void block_reduce(fr (&acc)[NS], fr* out) {
+    __shared__ fr warp_sums[32 * NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++)
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) acc[s] = fr_add(acc[s], fr_shfl_down(acc[s], d));
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    if (lane == 0)
+#pragma unroll
+        for (int s = 0; s < NS; s++) warp_sums[warp * NS + s] = acc[s];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            fr v = lane < nwarps ? warp_sums[lane * NS + s] : fr_zero();
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) v = fr_add(v, fr_shfl_down(v, d));
+            if (lane == 0) fr_store(&out[s], v);
+        }
+    }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(256) k_reduce_partials(const fr* __restrict__ partials, int nblocks, fr* result) {
+    fr acc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) acc[s] = fr_zero();
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
+#pragma unroll
+        for (int s = 0; s < NS; s++) acc[s] = fr_add(acc[s], fr_load(&partials[b * NS + s]));
+    block_reduce<NS>(acc, result);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Skyscraper compress_many  (seam: CompressManyFn)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_compress_many(const fr* __restrict__ msgs, fr* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr l = sky_reduce(fr_load_nc(&msgs[2 * i]));
+    fr r = sky_reduce(fr_load_nc(&msgs[2 * i + 1]));
+    fr_store(&out[i], sky_compress(l, r));
+}
+int launch_compress_many(cudaStream_t st, const void* msgs, void* hashes, size_t n) {
+    if (n == 0) return 0;
+    k_compress_many<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const fr*)msgs, (fr*)hashes, n);
+    return 1;
+}
+
+__global__ void k_convert(fr* data, size_t n, bool to_mont) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr x = fr_load(&data[i]);
+    fr_store(&data[i], to_mont ? fr_to_mont(fr_reduce_any(x)) : fr_from_mont(x));
+}
+int launch_to_mont(cudaStream_t st, void* data, size_t n, bool to_mont) {
+    if (n == 0) return 0;
+    k_convert<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((fr*)data, n, to_mont);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0 wavelet (evaluations <-> coefficients): add/sub butterflies only, HBM bound; tiled in shared
+// memory so a 2^21 vector is 2 passes over HBM instead of 21.
+// ------------------------------------------------------------------------------------------------
+constexpr int WAVELET_FLAT_BITS = 11;  // 2^11 x 32 B = 64 KB tile
+constexpr int WAVELET_ROW_BITS = 7;    // 2^7 rows x 16 cols x 32 B = 64 KB tile
+
+template <bool INV>
+__global__ void __launch_bounds__(512) k_wavelet_flat(fr* a, int bits) {
+    extern __shared__ uint4 smem_raw[];
+    fr* sm = reinterpret_cast<fr*>(smem_raw);
+    size_t base = (size_t)blockIdx.x << bits;
+    int n = 1 << bits;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = fr_load(&a[base + i]);
+    __syncthreads();
+    for (int hb = 0; hb < bits; hb++) {
+        int h = 1 << hb;
+        for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
+            int i = ((t >> hb) << (hb + 1)) | (t & (h - 1));
+            fr lo = sm[i], hi = sm[i + h];
+            sm[i + h] = INV ? fr_sub(hi, lo) : fr_add(hi, lo);
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) fr_store(&a[base + i], sm[i]);
+}
+// rows at stride 2^l elements, S row bits, 16 contiguous columns per row
+template <bool INV>
+__global__ void __launch_bounds__(512) k_wavelet_rows(fr* a, int l, int S) {
+    extern __shared__ uint4 smem_raw[];
+    fr* sm = reinterpret_cast<fr*>(smem_raw);
+    size_t tile = blockIdx.x;
+    size_t lowgrp = tile & (((size_t)1 << (l - 4)) - 1);
+    size_t hi = tile >> (l - 4);
+    size_t base = (hi << (l + S)) | (lowgrp << 4);
+    int rows = 1 << S;
+    for (int idx = threadIdx.x; idx < rows * 16; idx += blockDim.x)
+        sm[idx] = fr_load(&a[base + ((size_t)(idx >> 4) << l) + (idx & 15)]);
+    __syncthreads();
+    for (int hb = 0; hb < S; hb++) {
+        int h = 1 << hb;
+        for (int t = threadIdx.x; t < (rows / 2) * 16; t += blockDim.x) {
+            int k = t & 15, b = t >> 4;
+            int i = ((b >> hb) << (hb + 1)) | (b & (h - 1));
+            fr lo = sm[i * 16 + k], hiv = sm[(i + h) * 16 + k];
+            sm[(i + h) * 16 + k] = INV ? fr_sub(hiv, lo) : fr_add(hiv, lo);
+        }
+        __syncthreads();
+    }
+    for (int idx = threadIdx.x; idx < rows * 16; idx += blockDim.x)
+        fr_store(&a[base + ((size_t)(idx >> 4) << l) + (idx & 15)], sm[idx]);
+}
+int launch_wavelet(cudaStream_t st, void* a, int log_n, bool inverse) {
+    int launches = 0;
+    int flat = log_n < WAVELET_FLAT_BITS ? log_n : WAVELET_FLAT_BITS;
+    size_t smem = ((size_t)32 << flat);
+    unsigned grid = 1u << (log_n - flat);
+    if (inverse)
+        k_wavelet_flat<true><<<grid, 512, smem, st>>>((fr*)a, flat);
+    else
+        k_wavelet_flat<false><<<grid, 512, smem, st>>>((fr*)a, flat);
+    launches++;
+    for (int l = flat; l < log_n;) {
+        int S = (log_n - l) < WAVELET_ROW_BITS ? (log_n - l) : WAVELET_ROW_BITS;
+        size_t sm2 = (size_t)32 * 16 << S;
+        unsigned g2 = 1u << (log_n - S - 4);
+        if (inverse)
+            k_wavelet_rows<true><<<g2, 512, sm2, st>>>((fr*)a, l, S);
+        else
+            k_wavelet_rows<false><<<g2, 512, sm2, st>>>((fr*)a, l, S);
+        launches++;
+        l += S;
+    }
+    return launches;
+}
+
+// ------------------------------------------------------------------------------------------------
+// twiddle table: W[e] = omega^e, omega = 2-adic root of order 2^log_m; pow2[b] = omega^(2^b) from host
+// ------------------------------------------------------------------------------------------------
+__constant__ uint32_t TW_POW2[28][8];
+__global__ void k_twiddle_table(fr* table, int log_m) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n = (size_t)1 << (log_m - 1);
+    if (e >= n) return;
+    fr acc = fr_one();
+    for (int b = 0; b < log_m - 1; b++)
+        if ((e >> b) & 1) {
+            fr w;
+#pragma unroll
+            for (int k = 0; k < 8; k++) w.v[k] = TW_POW2[b][k];
+            acc = fr_mul(acc, w);
+        }
+    fr_store(&table[e], acc);
+}
+// host supplies omega^(2^b) for b = 0..log_m-2 via cudaMemcpyToSymbol before calling (pkwhir.cu)
+cudaError_t set_twiddle_pow2(const uint32_t* host_pow2, int count) {
+    return cudaMemcpyToSymbol(TW_POW2, host_pow2, (size_t)count * 32);
+}
+int launch_twiddle_table(cudaStream_t st, void* table, int log_m) {
+    if (log_m < 1) return 0;
+    size_t n = (size_t)1 << (log_m - 1);
+    k_twiddle_table<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((fr*)table, log_m);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 Reed-Solomon encode: 16 column NTTs ("prover helps" layout), E coset NTTs of size N' per column,
+// multi-pass radix-2 DIF in shared-memory tiles of 2^S points x 16 columns.
+// ------------------------------------------------------------------------------------------------
+constexpr int NTT_TILE_BITS = 7;  // 2^7 points x 16 columns x 32 B = 64 KB
+struct NttPass {
+    const fr* in;
+    fr* out;
+    const fr* W;       // twiddle table, order 2^tbl_log
+    int tbl_shift;     // omega_M^e = W[e << tbl_shift]
+    int L, l, S, logE, logM;
+    int first, last;
+    size_t leaf_stride, col_offset;
+};
+__global__ void __launch_bounds__(512) k_ntt_pass(NttPass P) {
+    extern __shared__ uint4 smem_raw[];
+    fr* sm = reinterpret_cast<fr*>(smem_raw);
+    const int S = P.S, l = P.l, L = P.L;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t s = tile >> (L - S);
+    const uint32_t t = tile & ((1u << (L - S)) - 1u);
+    const uint32_t Lo = t & ((1u << l) - 1u);
+    const uint32_t H = t >> l;
+    const uint32_t qbase = (H << (l + S)) | Lo;
+    const int npts = 1 << S;
+    const uint32_t halfM = 1u << (P.logM - 1);
+    for (int idx = threadIdx.x; idx < npts * 16; idx += blockDim.x) {
+        uint32_t mid = idx >> 4, k = idx & 15;
+        uint32_t q = qbase | (mid << l);
+        fr x;
+        if (P.first) {
+            x = fr_load_nc(&P.in[(size_t)q * 16 + k]);
+            if (s) {  // coset twist omega_M^(s*q)
+                uint32_t e = s * q;
+                bool neg = e >= halfM;
+                e &= halfM - 1;
+                if (e) x = fr_mul(x, fr_load_nc(&P.W[(size_t)e << P.tbl_shift]));
+                if (neg) x = fr_neg(x);
+            }
+        } else {
+            x = fr_load(&P.in[(((size_t)s << L) + q) * 16 + k]);
+        }
+        sm[idx] = x;
+    }
+    __syncthreads();
+    for (int hb = S - 1; hb >= 0; hb--) {
+        const int h = 1 << hb;
+        const int esh = L - 1 - hb - l + P.logE;
+        for (int bf = threadIdx.x; bf < (npts / 2) * 16; bf += blockDim.x) {
+            int k = bf & 15, b = bf >> 4;
+            int j = b & (h - 1);
+            int i0 = ((b >> hb) << (hb + 1)) | j;
+            int i1 = i0 + h;
+            uint32_t e = (((uint32_t)j << l) | Lo) << esh;
+            fr a = sm[i0 * 16 + k], bb = sm[i1 * 16 + k];
+            sm[i0 * 16 + k] = fr_add(a, bb);
+            fr d = fr_sub(a, bb);
+            if (e) d = fr_mul(d, fr_load_nc(&P.W[(size_t)e << P.tbl_shift]));
+            sm[i1 * 16 + k] = d;
+        }
+        __syncthreads();
+    }
+    for (int idx = threadIdx.x; idx < npts * 16; idx += blockDim.x) {
+        uint32_t mid = idx >> 4, k = idx & 15;
+        uint32_t q = qbase | (mid << l);
+        if (P.last) {
+            uint32_t tq = L ? (__brev(q) >> (32 - L)) : 0u;
+            size_t row = (size_t)s + ((size_t)tq << P.logE);
+            fr_store(&P.out[row * P.leaf_stride + P.col_offset + k], sm[idx]);
+        } else {
+            fr_store(&P.out[(((size_t)s << L) + q) * 16 + k], sm[idx]);
+        }
+    }
+}
+int launch_rs_encode(cudaStream_t st, const void* coeffs, int log_n, int log_inv_rate, int fold, void* out,
+                     size_t leaf_stride, size_t col_offset, void* scratch, const void* table, int table_log_m) {
+    // fold must be 4 (16 columns): FoldingFactor::Constant(4), provekit/r1cs-compiler/src/whir_r1cs.rs:44
+    int L = log_n - fold;
+    int logE = log_inv_rate;
+    int logM = L + logE;
+    int launches = 0;
+    int done = 0;  // stage bits processed, from the top
+    int npass = L == 0 ? 1 : (L + NTT_TILE_BITS - 1) / NTT_TILE_BITS;
+    for (int p = 0; p < npass; p++) {
+        int S = L - done < NTT_TILE_BITS ? L - done : NTT_TILE_BITS;
+        NttPass P;
+        P.first = p == 0;
+        P.last = p == npass - 1;
+        P.in = (const fr*)(P.first ? coeffs : scratch);
+        P.out = (fr*)(P.last ? out : scratch);
+        P.W = (const fr*)table;
+        P.tbl_shift = table_log_m - logM;
+        P.L = L;
+        P.S = S;
+        P.l = L - done - S;
+        P.logE = logE;
+        P.logM = logM < 1 ? 1 : logM;
+        P.leaf_stride = leaf_stride;
+        P.col_offset = col_offset;
+        unsigned grid = 1u << (logE + L - S);
+        size_t smem = (size_t)32 * 16 << S;
+        k_ntt_pass<<<grid, S >= 6 ? 512 : (S >= 4 ? 128 : 32), smem, st>>>(P);
+        launches++;
+        done += S;
+    }
+    return launches;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 Merkle tree: leaf digest = left fold of compress over the leaf (SkyscraperCRH, provekit/common/
+// src/skyscraper/whir.rs:30-48), inner nodes = compress(left, right) (:53-74).  Digests are kept
+// CANONICAL on device (that is the form compress consumes and the transcript carries).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_merkle_leaves(const fr* __restrict__ leaves, size_t L, int w, fr* nodes) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L) return;
+    const fr* leaf = leaves + i * w;
+    fr d = fr_from_mont(fr_load_nc(&leaf[0]));
+    for (int k = 1; k < w; k++) d = sky_compress(d, fr_from_mont(fr_load_nc(&leaf[k])));
+    fr_store(&nodes[L + i], d);
+}
+__global__ void __launch_bounds__(128) k_merkle_level(fr* nodes, size_t lvl) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= lvl) return;
+    size_t node = lvl + i;
+    fr_store(&nodes[node], sky_compress(fr_load(&nodes[2 * node]), fr_load(&nodes[2 * node + 1])));
+}
+// all levels from `top` (<= 256 nodes) down to the root in one block
+__global__ void __launch_bounds__(256) k_merkle_top(fr* nodes, int top) {
+    for (int lvl = top; lvl >= 1; lvl >>= 1) {
+        if ((int)threadIdx.x < lvl) {
+            int node = lvl + threadIdx.x;
+            fr_store(&nodes[node], sky_compress(fr_load(&nodes[2 * node]), fr_load(&nodes[2 * node + 1])));
+        }
+        __syncthreads();
+    }
+}
+int launch_merkle(cudaStream_t st, const void* leaves, size_t L, size_t w, void* nodes) {
+    int launches = 0;
+    k_merkle_leaves<<<(unsigned)((L + 127) / 128), 128, 0, st>>>((const fr*)leaves, L, (int)w, (fr*)nodes);
+    launches++;
+    size_t lvl = L / 2;
+    for (; lvl > 256; lvl >>= 1) {
+        k_merkle_level<<<(unsigned)((lvl + 127) / 128), 128, 0, st>>>((fr*)nodes, lvl);
+        launches++;
+    }
+    if (lvl >= 1) {
+        k_merkle_top<<<1, 256, 0, st>>>((fr*)nodes, (int)lvl);
+        launches++;
+    }
+    return launches;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor-product tables (eq / power tables), accumulate, dot products
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_tensor_tables(const fr* __restrict__ points, int pt_stride, int var_off,
+                                                       int nv, const fr* __restrict__ scales, bool eq_mode, fr* out) {
+    size_t k = blockIdx.x;
+    fr* T = out + (k << nv);
+    if (threadIdx.x == 0) fr_store(&T[0], scales ? fr_load(&scales[k]) : fr_one());
+    __syncthreads();
+    int len = 1;
+    for (int j = nv - 1; j >= 0; j--) {  // last variable <-> least significant index bit
+        fr x = fr_load(&points[k * pt_stride + var_off + j]);
+        for (int i = threadIdx.x; i < len; i += blockDim.x) {
+            fr t = fr_load(&T[i]);
+            fr s1 = fr_mul(t, x);
+            fr_store(&T[i + len], s1);
+            if (eq_mode) fr_store(&T[i], fr_sub(t, s1));
+        }
+        len <<= 1;
+        __syncthreads();
+    }
+}
+int launch_tensor_tables(cudaStream_t st, const void* points, size_t K, int pt_stride, int var_off, int nv,
+                         const void* scales, bool eq_mode, void* out) {
+    if (K == 0) return 0;
+    k_tensor_tables<<<(unsigned)K, 256, 0, st>>>((const fr*)points, pt_stride, var_off, nv, (const fr*)scales, eq_mode,
+                                                 (fr*)out);
+    return 1;
+}
+__global__ void __launch_bounds__(256) k_tensor_accumulate(fr* out, size_t n, const fr* __restrict__ hi,
+                                                           const fr* __restrict__ lo, int K, int lo_bits, int hi_bits) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    size_t ih = idx >> lo_bits, il = idx & (((size_t)1 << lo_bits) - 1);
+    fr acc = fr_load(&out[idx]);
+    for (int k = 0; k < K; k++) {
+        fr h = fr_load_nc(&hi[((size_t)k << hi_bits) + ih]);
+        fr l = fr_load_nc(&lo[((size_t)k << lo_bits) + il]);
+        acc = fr_add(acc, fr_mul(h, l));
+    }
+    fr_store(&out[idx], acc);
+}
+int launch_tensor_accumulate(cudaStream_t st, void* out, int log_n, const void* hi, const void* lo, size_t K,
+                             int lo_bits) {
+    size_t n = (size_t)1 << log_n;
+    k_tensor_accumulate<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((fr*)out, n, (const fr*)hi, (const fr*)lo, (int)K,
+                                                                     lo_bits, log_n - lo_bits);
+    return 1;
+}
+__global__ void __launch_bounds__(256) k_tensor_dot(const fr* __restrict__ a, size_t n, const fr* __restrict__ hi,
+                                                    const fr* __restrict__ lo, int lo_bits, fr* partials) {
+    fr acc[1] = {fr_zero()};
+    size_t mask = ((size_t)1 << lo_bits) - 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        fr t = fr_mul(fr_load_nc(&hi[i >> lo_bits]), fr_load_nc(&lo[i & mask]));
+        acc[0] = fr_add(acc[0], fr_mul(fr_load_nc(&a[i]), t));
+    }
+    block_reduce<1>(acc, &partials[blockIdx.x]);
+}
+int launch_tensor_dot(cudaStream_t st, const void* a, size_t n, const void* hi, const void* lo, int lo_bits,
+                      void* partials, void* result) {
+    int g = grid_for(n, 256, REDUCE_MAX_BLOCKS);
+    k_tensor_dot<<<g, 256, 0, st>>>((const fr*)a, n, (const fr*)hi, (const fr*)lo, lo_bits, (fr*)partials);
+    k_reduce_partials<1><<<1, 256, 0, st>>>((const fr*)partials, g, (fr*)result);
+    return 2;
+}
+__global__ void __launch_bounds__(256) k_dot(const fr* __restrict__ a, const fr* __restrict__ b, size_t n, fr* partials) {
+    fr acc[1] = {fr_zero()};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        acc[0] = fr_add(acc[0], fr_mul(fr_load_nc(&a[i]), fr_load_nc(&b[i])));
+    block_reduce<1>(acc, &partials[blockIdx.x]);
+}
+int launch_dot(cudaStream_t st, const void* a, const void* b, size_t n, void* partials, void* result) {
+    int g = grid_for(n, 256, REDUCE_MAX_BLOCKS);
+    k_dot<<<g, 256, 0, st>>>((const fr*)a, (const fr*)b, n, (fr*)partials);
+    k_reduce_partials<1><<<1, 256, 0, st>>>((const fr*)partials, g, (fr*)result);
+    return 2;
+}
+__global__ void __launch_bounds__(256) k_axpy(fr* y, const fr* __restrict__ x, fr_arg a, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr_store(&y[i], fr_add(fr_load(&y[i]), fr_mul(arg_fr(a), fr_load_nc(&x[i]))));
+}
+int launch_axpy(cudaStream_t st, void* y, const void* x, fr_arg a, size_t n) {
+    if (n == 0) return 0;
+    k_axpy<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((fr*)y, (const fr*)x, a, n);
+    return 1;
+}
+// K8: 2^k consecutive coefficients -> multilinear value, r[j] binds bit j (k <= 4)
+__global__ void __launch_bounds__(128) k_fold_coeffs(const fr* __restrict__ c, size_t nout, const fr* __restrict__ r,
+                                                     int k, fr* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nout) return;
+    int w = 1 << k;
+    fr tmp[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+        if (j < w) tmp[j] = fr_load_nc(&c[i * w + j]);
+    int len = w;
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+        if (v < k) {
+            fr rv = fr_load_nc(&r[v]);
+            len >>= 1;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (j < len) tmp[j] = fr_add(tmp[2 * j], fr_mul(rv, tmp[2 * j + 1]));
+        }
+    }
+    fr_store(&out[i], tmp[0]);
+}
+int launch_fold_coeffs(cudaStream_t st, const void* coeffs, int log_n, const void* r_dev, int k, void* out) {
+    size_t nout = (size_t)1 << (log_n - k);
+    k_fold_coeffs<<<(unsigned)((nout + 127) / 128), 128, 0, st>>>((const fr*)coeffs, nout, (const fr*)r_dev, k, (fr*)out);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5 zk-sumcheck round: fused fold + map + reduce (provekit/common/src/utils/sumcheck.rs:16-104 with
+// the map of provekit/prover/src/whir_r1cs.rs:284-291).  MSB pairing: i <-> i + len/2.
+// ------------------------------------------------------------------------------------------------
+template <bool FOLD>
+__global__ void __launch_bounds__(256) k_zk_sumcheck(fr* a, fr* b, fr* c, fr* eq, size_t half, fr_arg foldv, fr* partials) {
+    // `half` = (length after folding) / 2; before folding the arrays are 4*half long
+    fr acc[3] = {fr_zero(), fr_zero(), fr_zero()};
+    fr f = arg_fr(foldv);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+        fr v0[4], v1[4];
+        fr* arr[4] = {a, b, c, eq};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (FOLD) {
+                fr x0 = fr_load(&arr[k][i]), x1 = fr_load(&arr[k][i + half]);
+                fr x2 = fr_load(&arr[k][i + 2 * half]), x3 = fr_load(&arr[k][i + 3 * half]);
+                v0[k] = fr_add(x0, fr_mul(f, fr_sub(x2, x0)));
+                v1[k] = fr_add(x1, fr_mul(f, fr_sub(x3, x1)));
+                fr_store(&arr[k][i], v0[k]);
+                fr_store(&arr[k][i + half], v1[k]);
+            } else {
+                v0[k] = fr_load(&arr[k][i]);
+                v1[k] = fr_load(&arr[k][i + half]);
+            }
+        }
+        const fr &a0 = v0[0], &a1 = v1[0], &b0 = v0[1], &b1 = v1[1], &c0 = v0[2], &c1 = v1[2], &e0 = v0[3], &e1 = v1[3];
+        fr f0 = fr_mul(e0, fr_sub(fr_mul(a0, b0), c0));
+        fr am = fr_sub(fr_dbl(a0), a1), bm = fr_sub(fr_dbl(b0), b1);
+        fr cm = fr_sub(fr_dbl(c0), c1), em = fr_sub(fr_dbl(e0), e1);
+        fr fm = fr_mul(em, fr_sub(fr_mul(am, bm), cm));
+        fr fi = fr_mul(fr_mul(fr_sub(e1, e0), fr_sub(a1, a0)), fr_sub(b1, b0));
+        acc[0] = fr_add(acc[0], f0);
+        acc[1] = fr_add(acc[1], fm);
+        acc[2] = fr_add(acc[2], fi);
+    }
+    block_reduce<3>(acc, &partials[blockIdx.x * 3]);
+}
+int launch_zk_sumcheck_round(cudaStream_t st, void* a, void* b, void* c, void* eq, int log_n, bool has_fold,
+                             fr_arg fold, void* partials, void* result) {
+    size_t n_after = (size_t)1 << (has_fold ? log_n - 1 : log_n);
+    size_t half = n_after / 2;
+    int g = grid_for(half, 256, REDUCE_MAX_BLOCKS);
+    if (has_fold)
+        k_zk_sumcheck<true><<<g, 256, 0, st>>>((fr*)a, (fr*)b, (fr*)c, (fr*)eq, half, fold, (fr*)partials);
+    else
+        k_zk_sumcheck<false><<<g, 256, 0, st>>>((fr*)a, (fr*)b, (fr*)c, (fr*)eq, half, fold, (fr*)partials);
+    k_reduce_partials<3><<<1, 256, 0, st>>>((const fr*)partials, g, (fr*)result);
+    return 2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7 WHIR sumcheck round [whir SumcheckSingle]: LSB pairing (2i, 2i+1), sends h(0), h(1), h(2).
+// ------------------------------------------------------------------------------------------------
+template <bool FOLD>
+__global__ void __launch_bounds__(256) k_whir_sumcheck(const fr* __restrict__ p_in, const fr* __restrict__ w_in,
+                                                       fr* p_out, fr* w_out, size_t pairs, fr_arg foldv, fr* partials) {
+    fr acc[3] = {fr_zero(), fr_zero(), fr_zero()};
+    fr f = arg_fr(foldv);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (size_t)gridDim.x * blockDim.x) {
+        fr p0, p1, w0, w1;
+        if (FOLD) {
+            fr x0 = fr_load_nc(&p_in[4 * i]), x1 = fr_load_nc(&p_in[4 * i + 1]);
+            fr x2 = fr_load_nc(&p_in[4 * i + 2]), x3 = fr_load_nc(&p_in[4 * i + 3]);
+            p0 = fr_add(x0, fr_mul(f, fr_sub(x1, x0)));
+            p1 = fr_add(x2, fr_mul(f, fr_sub(x3, x2)));
+            fr_store(&p_out[2 * i], p0);
+            fr_store(&p_out[2 * i + 1], p1);
+            x0 = fr_load_nc(&w_in[4 * i]); x1 = fr_load_nc(&w_in[4 * i + 1]);
+            x2 = fr_load_nc(&w_in[4 * i + 2]); x3 = fr_load_nc(&w_in[4 * i + 3]);
+            w0 = fr_add(x0, fr_mul(f, fr_sub(x1, x0)));
+            w1 = fr_add(x2, fr_mul(f, fr_sub(x3, x2)));
+            fr_store(&w_out[2 * i], w0);
+            fr_store(&w_out[2 * i + 1], w1);
+        } else {
+            p0 = fr_load_nc(&p_in[2 * i]); p1 = fr_load_nc(&p_in[2 * i + 1]);
+            w0 = fr_load_nc(&w_in[2 * i]); w1 = fr_load_nc(&w_in[2 * i + 1]);
+        }
+        acc[0] = fr_add(acc[0], fr_mul(p0, w0));
+        acc[1] = fr_add(acc[1], fr_mul(p1, w1));
+        acc[2] = fr_add(acc[2], fr_mul(fr_sub(fr_dbl(p1), p0), fr_sub(fr_dbl(w1), w0)));
+    }
+    block_reduce<3>(acc, &partials[blockIdx.x * 3]);
+}
+int launch_whir_sumcheck_round(cudaStream_t st, const void* p_in, const void* w_in, void* p_out, void* w_out,
+                               int log_n, bool has_fold, fr_arg fold, void* partials, void* result) {
+    size_t n_after = (size_t)1 << (has_fold ? log_n - 1 : log_n);
+    size_t pairs = n_after / 2;
+    int g = grid_for(pairs, 256, REDUCE_MAX_BLOCKS);
+    if (has_fold)
+        k_whir_sumcheck<true><<<g, 256, 0, st>>>((const fr*)p_in, (const fr*)w_in, (fr*)p_out, (fr*)w_out, pairs, fold,
+                                                 (fr*)partials);
+    else
+        k_whir_sumcheck<false><<<g, 256, 0, st>>>((const fr*)p_in, (const fr*)w_in, (fr*)p_out, (fr*)w_out, pairs, fold,
+                                                  (fr*)partials);
+    k_reduce_partials<3><<<1, 256, 0, st>>>((const fr*)partials, g, (fr*)result);
+    return 2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K10 gathers for STIR answers / Merkle multipaths
+// ------------------------------------------------------------------------------------------------
+__global__ void k_gather_rows(const fr* __restrict__ leaves, size_t w, const uint64_t* __restrict__ idx, size_t n_idx,
+                              fr* out) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_idx * w) return;
+    size_t q = t / w, k = t % w;
+    fr_store(&out[t], fr_load_nc(&leaves[idx[q] * w + k]));
+}
+int launch_gather_rows(cudaStream_t st, const void* leaves, size_t w, const uint64_t* idx_dev, size_t n_idx, void* out) {
+    size_t n = n_idx * w;
+    if (n == 0) return 0;
+    k_gather_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const fr*)leaves, w, idx_dev, n_idx, (fr*)out);
+    return 1;
+}
+__global__ void k_gather_paths(const fr* __restrict__ nodes, size_t L, const uint64_t* __restrict__ idx, size_t n_idx,
+                               int depth, fr* out) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_idx * depth) return;
+    size_t q = t / depth;
+    int d = (int)(t % depth);
+    size_t pos = (L + idx[q]) >> d;
+    fr_store(&out[t], fr_load_nc(&nodes[pos ^ 1]));
+}
+int launch_gather_paths(cudaStream_t st, const void* nodes, size_t L, const uint64_t* idx_dev, size_t n_idx, int depth,
+                        void* out) {
+    size_t n = n_idx * depth;
+    if (n == 0) return 0;
+    k_gather_paths<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const fr*)nodes, L, idx_dev, n_idx, depth, (fr*)out);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PoW grinding (skyscraper/core/src/pow.rs:24-41, generic.rs:42-71): accept iff
+// compress(challenge, [nonce,0,0,0]) < threshold; the smallest accepted nonce wins (fetch_min).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_pow_scan(fr_arg challenge, fr_arg threshold, uint64_t base, uint64_t count,
+                                                  unsigned long long* best) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    uint64_t nonce = base + t;
+    fr l = sky_reduce(arg_fr(challenge));
+    fr r = fr_zero();
+    r.v[0] = (uint32_t)nonce;
+    r.v[1] = (uint32_t)(nonce >> 32);
+    fr h = sky_compress(l, r);
+    fr thr = arg_fr(threshold);
+    bool less = false;
+#pragma unroll
+    for (int i = 7; i >= 0; i--) {
+        if (h.v[i] != thr.v[i]) {
+            less = h.v[i] < thr.v[i];
+            break;
+        }
+    }
+    if (less) atomicMin(best, (unsigned long long)nonce);
+}
+int launch_pow_scan(cudaStream_t st, fr_arg challenge, fr_arg threshold, uint64_t base, uint64_t count,
+                    unsigned long long* best) {
+    k_pow_scan<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(challenge, threshold, base, count, best);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// microbenchmark: modmul/s ceiling of the integer pipe (two independent chains per thread)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_modmul_bench(fr* data, int iters) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    fr x = fr_load(&data[2 * i]), y = fr_load(&data[2 * i + 1]);
+    for (int it = 0; it < iters; it++) {
+        x = fr_mul(x, y);
+        y = fr_mul(y, x);
+    }
+    fr_store(&data[2 * i], x);
+    fr_store(&data[2 * i + 1], y);
+}
+int launch_modmul_bench(cudaStream_t st, void* data, size_t n_threads, int iters) {
+    k_modmul_bench<<<(unsigned)(n_threads / 256), 256, 0, st>>>((fr*)data, iters);
+    return 1;
+}
+
+cudaError_t init_kernel_attributes() {
+    cudaError_t e;
+    const int smem = 64 * 1024;
+    if ((e = cudaFuncSetAttribute(k_wavelet_flat<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+    if ((e = cudaFuncSetAttribute(k_wavelet_flat<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+    if ((e = cudaFuncSetAttribute(k_wavelet_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+    if ((e = cudaFuncSetAttribute(k_wavelet_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+    if ((e = cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+    return cudaSuccess;
+}
+
+}  // namespace pk

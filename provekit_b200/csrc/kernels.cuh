@@ -1,0 +1,73 @@
+// provekit_b200/csrc/kernels.cuh — launchers of the sm_100a kernels (K0..K10 of SURVEY §3, PoW).
+// All pointers are device pointers to 32-byte field elements unless noted.  Every launcher enqueues on
+// `st` and returns the number of kernels it launched (for pk_launch_count).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pk {
+
+struct fr;
+
+// fold parameter for the sumchecks and scalars in general are passed by value as 8 limbs
+struct fr_arg {
+    uint32_t v[8];
+};
+
+int launch_compress_many(cudaStream_t st, const void* msgs, void* hashes, size_t n);
+int launch_to_mont(cudaStream_t st, void* data, size_t n, bool to_mont);
+
+// K0 wavelet transforms, in place
+int launch_wavelet(cudaStream_t st, void* a, int log_n, bool inverse);
+
+// twiddle table W[e] = omega_M^e (Montgomery), e < M/2, omega_M = arkworks 2-adic root of order M = 2^log_m
+int launch_twiddle_table(cudaStream_t st, void* table, int log_m);
+
+// K1 RS encode: coeffs (2^log_n) -> out[(row)*leaf_stride + col_offset + k]; scratch: 2^(log_n+log_inv_rate)
+// table: twiddles for M = 2^(log_n + log_inv_rate - fold), table_log_m >= that (strided use)
+int launch_rs_encode(cudaStream_t st, const void* coeffs, int log_n, int log_inv_rate, int fold, void* out,
+                     size_t leaf_stride, size_t col_offset, void* scratch, const void* table, int table_log_m);
+
+// K2 Merkle: leaves Montgomery, nodes canonical heap order
+int launch_merkle(cudaStream_t st, const void* leaves, size_t L, size_t w, void* nodes);
+
+// tensor-product tables: for point k (k < K) and variable j (j < nv, point[k*pt_stride + var_off + j]):
+//   T_k[idx] = scale_k * prod_j (bit_{nv-1-j}(idx) ? f1 : f0),   eq: (f0,f1) = (1-x, x);  pow: (1, x)
+// scales may be null (=1).  out: K tables of 2^nv.
+int launch_tensor_tables(cudaStream_t st, const void* points, size_t K, int pt_stride, int var_off, int nv,
+                         const void* scales, bool eq_mode, void* out);
+// out[idx] += sum_k hi_k[idx >> lo_bits] * lo_k[idx & mask]
+int launch_tensor_accumulate(cudaStream_t st, void* out, int log_n, const void* hi, const void* lo, size_t K,
+                             int lo_bits);
+// result[0] = sum_idx a[idx] * hi[idx >> lo_bits] * lo[idx & mask]   (hi/lo single tables)
+int launch_tensor_dot(cudaStream_t st, const void* a, size_t n, const void* hi, const void* lo, int lo_bits,
+                      void* partials, void* result);
+// result[0] = <a, b>
+int launch_dot(cudaStream_t st, const void* a, const void* b, size_t n, void* partials, void* result);
+int launch_axpy(cudaStream_t st, void* y, const void* x, fr_arg a, size_t n);
+int launch_fold_coeffs(cudaStream_t st, const void* coeffs, int log_n, const void* r_dev, int k, void* out);
+
+// K5 / K7 sumcheck rounds; result: 3 field elements on device
+int launch_zk_sumcheck_round(cudaStream_t st, void* a, void* b, void* c, void* eq, int log_n, bool has_fold,
+                             fr_arg fold, void* partials, void* result);
+int launch_whir_sumcheck_round(cudaStream_t st, const void* p_in, const void* w_in, void* p_out, void* w_out,
+                               int log_n, bool has_fold, fr_arg fold, void* partials, void* result);
+
+// K10 gathers
+int launch_gather_rows(cudaStream_t st, const void* leaves, size_t w, const uint64_t* idx_dev, size_t n_idx,
+                       void* out);
+// out[q*depth + d]: d = 0 leaf sibling, then siblings going up (leaf -> root), canonical->canonical
+int launch_gather_paths(cudaStream_t st, const void* nodes, size_t L, const uint64_t* idx_dev, size_t n_idx,
+                        int depth, void* out);
+
+// PoW: scans nonces [base, base+count) and atomically mins accepted ones into *best (u64 on device)
+int launch_pow_scan(cudaStream_t st, fr_arg challenge, fr_arg threshold, uint64_t base, uint64_t count,
+                    unsigned long long* best);
+
+// microbenchmark: chains `iters` dependent Montgomery multiplications per thread; returns launches
+int launch_modmul_bench(cudaStream_t st, void* data, size_t n_threads, int iters);
+
+constexpr int REDUCE_MAX_BLOCKS = 1184;  // 148 SMs x 8
+
+}  // namespace pk

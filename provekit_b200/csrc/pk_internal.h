@@ -1,0 +1,82 @@
+// provekit_b200/csrc/pk_internal.h — private state behind the opaque handles of include/pkwhir.h
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/pkwhir.h"
+#include "kernels.cuh"
+
+struct pk_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    // small fixed work areas
+    void* d_partials = nullptr;   // REDUCE_MAX_BLOCKS * 3 field elements
+    void* d_result = nullptr;     // 64 field elements
+    uint64_t* h_result = nullptr; // pinned, 64 field elements
+    unsigned long long* d_best = nullptr;
+    // grow-on-demand work areas
+    void* d_twiddles = nullptr;
+    int twiddle_log_m = 0;
+    void* d_scratch = nullptr;    // NTT scratch
+    size_t scratch_elems = 0;
+    void* d_tables = nullptr;     // tensor tables / small uploads
+    size_t tables_elems = 0;
+    void* d_small = nullptr;      // points / scalars / indexes staging (bytes)
+    size_t small_bytes = 0;
+    void* h_stage = nullptr;      // pinned staging for uploads/downloads
+    size_t h_stage_bytes = 0;
+};
+
+struct pk_buf {
+    void* d = nullptr;
+    size_t n = 0;
+};
+
+struct pk_commitment {
+    void* leaves = nullptr;  // L * w field elements, Montgomery
+    void* nodes = nullptr;   // 2L field elements, canonical digests, heap order
+    size_t L = 0, w = 0;
+    int depth = 0;
+};
+
+namespace pk {
+int set_err(pk_ctx* ctx, int code, const char* fmt, ...);
+int ensure_twiddles(pk_ctx* ctx, int log_m);
+int ensure_scratch(pk_ctx* ctx, size_t elems);
+int ensure_tables(pk_ctx* ctx, size_t elems);
+int ensure_small(pk_ctx* ctx, size_t bytes);
+int ensure_stage(pk_ctx* ctx, size_t bytes);
+cudaError_t set_twiddle_pow2(const uint32_t* host_pow2, int count);
+cudaError_t init_kernel_attributes();
+inline fr_arg to_arg(const uint64_t x[4]) {
+    fr_arg a;
+    for (int i = 0; i < 4; i++) {
+        a.v[2 * i] = (uint32_t)x[i];
+        a.v[2 * i + 1] = (uint32_t)(x[i] >> 32);
+    }
+    return a;
+}
+}  // namespace pk
+
+#define PK_CUDA(ctx, call)                                                                          \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return pk::set_err(ctx, e__ == cudaErrorMemoryAllocation ? PK_ERR_OOM : PK_ERR_CUDA,    \
+                               "%s failed: %s", #call, cudaGetErrorString(e__));                    \
+    } while (0)
+#define PK_CHECK(ctx, cond, ...)                                                 \
+    do {                                                                         \
+        if (!(cond)) return pk::set_err(ctx, PK_ERR_INVALID_ARG, __VA_ARGS__);   \
+    } while (0)
+#define PK_TRY(expr)              \
+    do {                          \
+        int rc__ = (expr);        \
+        if (rc__ != PK_OK) return rc__; \
+    } while (0)

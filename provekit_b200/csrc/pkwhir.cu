@@ -1,0 +1,518 @@
+// provekit_b200/csrc/pkwhir.cu — the C-ABI of include/pkwhir.h over the sm_100a kernels.
+// No CPU fallback: every compute entry point launches CUDA kernels on ctx->stream or fails.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "host/fr_host.h"
+#include "pk_internal.h"
+
+namespace pk {
+
+int set_err(pk_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+static int grow(pk_ctx* ctx, void** p, size_t* cur, size_t want, size_t unit) {
+    if (*cur >= want) return PK_OK;
+    PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cur = 0;
+    PK_CUDA(ctx, cudaMalloc(p, want * unit));
+    *cur = want;
+    return PK_OK;
+}
+int ensure_scratch(pk_ctx* ctx, size_t elems) { return grow(ctx, &ctx->d_scratch, &ctx->scratch_elems, elems, 32); }
+int ensure_tables(pk_ctx* ctx, size_t elems) { return grow(ctx, &ctx->d_tables, &ctx->tables_elems, elems, 32); }
+int ensure_small(pk_ctx* ctx, size_t bytes) { return grow(ctx, &ctx->d_small, &ctx->small_bytes, bytes, 1); }
+int ensure_stage(pk_ctx* ctx, size_t bytes) {
+    if (ctx->h_stage_bytes >= bytes) return PK_OK;
+    PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    ctx->h_stage = nullptr;
+    ctx->h_stage_bytes = 0;
+    PK_CUDA(ctx, cudaMallocHost(&ctx->h_stage, bytes));
+    ctx->h_stage_bytes = bytes;
+    return PK_OK;
+}
+
+// twiddle table for the largest M seen so far; smaller domains use it strided (omega_{M/2} = omega_M^2)
+int ensure_twiddles(pk_ctx* ctx, int log_m) {
+    if (log_m < 1) log_m = 1;
+    if (ctx->twiddle_log_m >= log_m) return PK_OK;
+    if (log_m > 28) return set_err(ctx, PK_ERR_INVALID_ARG, "domain 2^%d exceeds the field's 2-adicity", log_m);
+    PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_twiddles) cudaFree(ctx->d_twiddles);
+    ctx->d_twiddles = nullptr;
+    ctx->twiddle_log_m = 0;
+    PK_CUDA(ctx, cudaMalloc(&ctx->d_twiddles, ((size_t)32 << (log_m - 1))));
+    uint32_t pow2[28][8];
+    pkh::Fr g = pkh::root_of_unity(log_m);
+    for (int b = 0; b < 28; b++) {
+        std::memcpy(pow2[b], g.l, 32);
+        g = pkh::sqr(g);
+    }
+    PK_CUDA(ctx, set_twiddle_pow2(&pow2[0][0], 28));
+    ctx->launches += launch_twiddle_table(ctx->stream, ctx->d_twiddles, log_m);
+    PK_CUDA(ctx, cudaGetLastError());
+    ctx->twiddle_log_m = log_m;
+    return PK_OK;
+}
+
+static int fetch_result(pk_ctx* ctx, uint64_t* out, int n_elems) {
+    PK_CUDA(ctx, cudaGetLastError());
+    PK_CUDA(ctx, cudaMemcpyAsync(ctx->h_result, ctx->d_result, (size_t)n_elems * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::memcpy(out, ctx->h_result, (size_t)n_elems * 32);
+    return PK_OK;
+}
+
+}  // namespace pk
+
+using namespace pk;
+
+extern "C" {
+
+const char* pk_version(void) { return "pkwhir 0.1 (sm_100a)"; }
+
+int pk_ctx_create(int device, pk_ctx** out) {
+    if (!out) return PK_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return PK_ERR_NO_DEVICE;
+    pk_ctx* ctx = new pk_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&ctx->d_partials, (size_t)REDUCE_MAX_BLOCKS * 3 * 32) != cudaSuccess ||
+        cudaMalloc(&ctx->d_result, 64 * 32) != cudaSuccess || cudaMallocHost((void**)&ctx->h_result, 64 * 32) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->d_best, 8) != cudaSuccess || init_kernel_attributes() != cudaSuccess) {
+        pk_ctx_destroy(ctx);
+        return PK_ERR_CUDA;
+    }
+    *out = ctx;
+    return PK_OK;
+}
+void pk_ctx_destroy(pk_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_partials);
+    cudaFree(ctx->d_result);
+    if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    cudaFree(ctx->d_best);
+    cudaFree(ctx->d_twiddles);
+    cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_tables);
+    cudaFree(ctx->d_small);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+const char* pk_last_error(const pk_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+uint64_t pk_launch_count(const pk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* pk_ctx_stream(pk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int pk_ctx_sync(pk_ctx* ctx) {
+    if (!ctx) return PK_ERR_INVALID_ARG;
+    PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PK_OK;
+}
+
+// ---- buffers -----------------------------------------------------------------------------------
+int pk_buf_alloc(pk_ctx* ctx, size_t n, pk_buf** out) {
+    if (!ctx || !out) return PK_ERR_INVALID_ARG;
+    *out = nullptr;
+    pk_buf* b = new pk_buf();
+    b->n = n;
+    cudaError_t e = cudaMalloc(&b->d, n ? n * 32 : 32);
+    if (e != cudaSuccess) {
+        delete b;
+        return set_err(ctx, PK_ERR_OOM, "cudaMalloc(%zu elems): %s", n, cudaGetErrorString(e));
+    }
+    *out = b;
+    return PK_OK;
+}
+void pk_buf_free(pk_ctx* ctx, pk_buf* b) {
+    if (!b) return;
+    if (ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(b->d);
+    delete b;
+}
+size_t pk_buf_len(const pk_buf* b) { return b ? b->n : 0; }
+void* pk_buf_device_ptr(pk_buf* b) { return b ? b->d : nullptr; }
+int pk_buf_upload(pk_ctx* ctx, pk_buf* dst, size_t off, const uint64_t* host, size_t n) {
+    PK_CHECK(ctx, dst && host && off + n <= dst->n, "pk_buf_upload: range out of bounds");
+    PK_CUDA(ctx, cudaMemcpyAsync((char*)dst->d + off * 32, host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PK_OK;
+}
+int pk_buf_download(pk_ctx* ctx, const pk_buf* src, size_t off, uint64_t* host, size_t n) {
+    PK_CHECK(ctx, src && host && off + n <= src->n, "pk_buf_download: range out of bounds");
+    PK_CUDA(ctx, cudaMemcpyAsync(host, (const char*)src->d + off * 32, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PK_OK;
+}
+int pk_buf_copy(pk_ctx* ctx, pk_buf* dst, size_t doff, const pk_buf* src, size_t soff, size_t n) {
+    PK_CHECK(ctx, dst && src && doff + n <= dst->n && soff + n <= src->n, "pk_buf_copy: range out of bounds");
+    PK_CUDA(ctx, cudaMemcpyAsync((char*)dst->d + doff * 32, (const char*)src->d + soff * 32, n * 32, cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+    return PK_OK;
+}
+int pk_buf_zero(pk_ctx* ctx, pk_buf* dst, size_t off, size_t n) {
+    PK_CHECK(ctx, dst && off + n <= dst->n, "pk_buf_zero: range out of bounds");
+    PK_CUDA(ctx, cudaMemsetAsync((char*)dst->d + off * 32, 0, n * 32, ctx->stream));
+    return PK_OK;
+}
+
+// ---- Skyscraper ----------------------------------------------------------------------------------
+int pk_skyscraper_compress_many(pk_ctx* ctx, const uint8_t* messages, uint8_t* hashes, size_t n) {
+    PK_CHECK(ctx, ctx && (n == 0 || (messages && hashes)), "compress_many: null buffer");
+    if (n == 0) return PK_OK;
+    // bounded device staging so arbitrarily large host batches stream through
+    const size_t CH = (size_t)1 << 22;
+    PK_TRY(ensure_scratch(ctx, 3 * (n < CH ? n : CH)));
+    for (size_t off = 0; off < n; off += CH) {
+        size_t m = n - off < CH ? n - off : CH;
+        char* d_msgs = (char*)ctx->d_scratch;
+        char* d_out = d_msgs + m * 64;
+        PK_CUDA(ctx, cudaMemcpyAsync(d_msgs, messages + off * 64, m * 64, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->launches += launch_compress_many(ctx->stream, d_msgs, d_out, m);
+        PK_CUDA(ctx, cudaGetLastError());
+        PK_CUDA(ctx, cudaMemcpyAsync(hashes + off * 32, d_out, m * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PK_OK;
+}
+int pk_skyscraper_compress_many_dev(pk_ctx* ctx, const pk_buf* messages, pk_buf* hashes, size_t n) {
+    PK_CHECK(ctx, messages && hashes && messages->n >= 2 * n && hashes->n >= n, "compress_many_dev: buffer too small");
+    ctx->launches += launch_compress_many(ctx->stream, messages->d, hashes->d, n);
+    PK_CUDA(ctx, cudaGetLastError());
+    return PK_OK;
+}
+
+// skyscraper/core/src/pow.rs:61-82
+static void f64_to_u256(double f, uint64_t out[4]) {
+    uint64_t bits;
+    std::memcpy(&bits, &f, 8);
+    bool sign = bits >> 63;
+    int exp_bits = (int)((bits >> 52) & 0x7ff);
+    uint64_t frac = bits & ((1ULL << 52) - 1);
+    int exp = exp_bits == 0 ? -1022 : exp_bits - 1023;
+    uint64_t sig = exp_bits == 0 ? frac : frac + (1ULL << 52);
+    std::memset(out, 0, 32);
+    if (sign) return;
+    if (exp > 256) {
+        std::memset(out, 0xff, 32);
+        return;
+    }
+    int shift = exp - 52;
+    if (shift < 0) {
+        out[0] = (uint64_t)std::round(f);
+    } else {
+        int limb = shift / 64, sh = shift % 64;
+        out[limb] = sig << sh;
+        if (sh != 0 && limb < 3) out[limb + 1] = sig >> (64 - sh);
+    }
+}
+int pk_pow_solve(pk_ctx* ctx, const uint64_t challenge[4], double bits, uint64_t* nonce) {
+    PK_CHECK(ctx, ctx && challenge && nonce, "pow_solve: null argument");
+    // provekit/common/src/skyscraper/pow.rs:16: assert!((0.0..60.0).contains(&bits))
+    PK_CHECK(ctx, bits >= 0.0 && bits < 60.0, "bits must be smaller than 60");
+    if (bits == 0.0) {  // pow.rs:34-36
+        *nonce = 0;
+        return PK_OK;
+    }
+    uint64_t thr[4];
+    double modulus = (double)pkh::P[3] * std::ldexp(1.0, 192);  // pow.rs:19
+    f64_to_u256(std::exp2(-(bits + 0.01)) * modulus, thr);      // PROVER_BIAS, pow.rs:6,37
+    unsigned long long init = ~0ULL;
+    PK_CUDA(ctx, cudaMemcpyAsync(ctx->d_best, &init, 8, cudaMemcpyHostToDevice, ctx->stream));
+    // chunk so that the expected number of chunks is ~1 and a chunk fills the machine
+    uint64_t chunk = (uint64_t)1 << 20;
+    double want = std::exp2(bits + 1.0);
+    while ((double)chunk < want && chunk < ((uint64_t)1 << 28)) chunk <<= 1;
+    for (uint64_t base = 0;; base += chunk) {
+        ctx->launches += launch_pow_scan(ctx->stream, to_arg(challenge), to_arg(thr), base, chunk, ctx->d_best);
+        PK_CUDA(ctx, cudaGetLastError());
+        PK_CUDA(ctx, cudaMemcpyAsync(ctx->h_result, ctx->d_best, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_result[0] != ~0ULL) {
+            *nonce = ctx->h_result[0];
+            return PK_OK;
+        }
+        if (base + chunk < base) return set_err(ctx, PK_ERR_INTERNAL, "pow_solve: nonce space exhausted");
+    }
+}
+
+// ---- wavelet -----------------------------------------------------------------------------------
+static int wavelet(pk_ctx* ctx, pk_buf* buf, int log_n, bool inverse) {
+    PK_CHECK(ctx, buf && log_n >= 0 && log_n < 40 && ((size_t)1 << log_n) <= buf->n, "wavelet: 2^%d exceeds buffer", log_n);
+    ctx->launches += launch_wavelet(ctx->stream, buf->d, log_n, inverse);
+    PK_CUDA(ctx, cudaGetLastError());
+    return PK_OK;
+}
+int pk_evals_to_coeffs(pk_ctx* ctx, pk_buf* buf, int log_n) { return wavelet(ctx, buf, log_n, true); }
+int pk_coeffs_to_evals(pk_ctx* ctx, pk_buf* buf, int log_n) { return wavelet(ctx, buf, log_n, false); }
+
+// ---- commit ------------------------------------------------------------------------------------
+static int rs_encode_raw(pk_ctx* ctx, const void* coeffs, int log_n, int log_inv_rate, int fold, void* leaves,
+                         size_t leaf_stride, size_t col_offset) {
+    PK_CHECK(ctx, fold == 4, "only FoldingFactor::Constant(4) is supported (r1cs-compiler/src/whir_r1cs.rs:44)");
+    PK_CHECK(ctx, log_n >= fold && log_inv_rate >= 0 && log_n + log_inv_rate <= 28, "rs_encode: bad sizes");
+    int logM = log_n - fold + log_inv_rate;
+    PK_TRY(ensure_twiddles(ctx, logM));
+    PK_TRY(ensure_scratch(ctx, (size_t)1 << (log_n + log_inv_rate)));
+    ctx->launches += launch_rs_encode(ctx->stream, coeffs, log_n, log_inv_rate, fold, leaves, leaf_stride, col_offset,
+                                      ctx->d_scratch, ctx->d_twiddles, ctx->twiddle_log_m);
+    PK_CUDA(ctx, cudaGetLastError());
+    return PK_OK;
+}
+int pk_rs_encode(pk_ctx* ctx, const pk_buf* coeffs, int log_n, int log_inv_rate, int fold, pk_buf* leaves,
+                 size_t leaf_stride, size_t col_offset) {
+    PK_CHECK(ctx, coeffs && leaves && log_n >= 0 && log_n < 40 && coeffs->n >= ((size_t)1 << log_n), "rs_encode: coeffs too small");
+    size_t rows = (size_t)1 << (log_n + log_inv_rate - fold);
+    PK_CHECK(ctx, col_offset + ((size_t)1 << fold) <= leaf_stride && leaves->n >= rows * leaf_stride, "rs_encode: leaves too small");
+    return rs_encode_raw(ctx, coeffs->d, log_n, log_inv_rate, fold, leaves->d, leaf_stride, col_offset);
+}
+int pk_merkle_build(pk_ctx* ctx, const pk_buf* leaves, size_t L, size_t w, pk_buf* nodes) {
+    PK_CHECK(ctx, leaves && nodes, "merkle_build: null buffer");
+    if (w == 0) return set_err(ctx, PK_ERR_EMPTY_INPUT, "IncorrectInputLength(0)");
+    PK_CHECK(ctx, L >= 2 && (L & (L - 1)) == 0, "merkle_build: leaf count must be a power of two >= 2");
+    PK_CHECK(ctx, leaves->n >= L * w && nodes->n >= 2 * L, "merkle_build: buffer too small");
+    ctx->launches += launch_merkle(ctx->stream, leaves->d, L, w, nodes->d);
+    PK_CUDA(ctx, cudaGetLastError());
+    return PK_OK;
+}
+int pk_commit_batch(pk_ctx* ctx, const pk_buf* const* coeffs, int batch, int log_n, int log_inv_rate, int fold,
+                    pk_commitment** out, uint64_t root_out[4]) {
+    PK_CHECK(ctx, ctx && coeffs && out && root_out && batch >= 1, "commit_batch: bad arguments");
+    PK_CHECK(ctx, fold == 4 && log_n >= fold && log_n + log_inv_rate - fold >= 1, "commit_batch: bad sizes");
+    for (int b = 0; b < batch; b++) PK_CHECK(ctx, coeffs[b] && coeffs[b]->n >= ((size_t)1 << log_n), "commit_batch: poly %d too small", b);
+    pk_commitment* c = new pk_commitment();
+    c->w = ((size_t)batch) << fold;
+    c->L = (size_t)1 << (log_n + log_inv_rate - fold);
+    c->depth = log_n + log_inv_rate - fold;
+    if (cudaMalloc(&c->leaves, c->L * c->w * 32) != cudaSuccess || cudaMalloc(&c->nodes, 2 * c->L * 32) != cudaSuccess) {
+        pk_commit_free(ctx, c);
+        return set_err(ctx, PK_ERR_OOM, "commit_batch: out of device memory");
+    }
+    for (int b = 0; b < batch; b++) {
+        int rc = rs_encode_raw(ctx, coeffs[b]->d, log_n, log_inv_rate, fold, c->leaves, c->w, (size_t)b << fold);
+        if (rc != PK_OK) {
+            pk_commit_free(ctx, c);
+            return rc;
+        }
+    }
+    ctx->launches += launch_merkle(ctx->stream, c->leaves, c->L, c->w, c->nodes);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_result, (char*)c->nodes + 32, 32, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        pk_commit_free(ctx, c);
+        return set_err(ctx, PK_ERR_CUDA, "commit_batch: %s", cudaGetErrorString(e));
+    }
+    pkh::Fr root = pkh::from_canonical(ctx->h_result);
+    std::memcpy(root_out, root.l, 32);
+    *out = c;
+    return PK_OK;
+}
+void pk_commit_free(pk_ctx* ctx, pk_commitment* c) {
+    if (!c) return;
+    if (ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(c->leaves);
+    cudaFree(c->nodes);
+    delete c;
+}
+size_t pk_commit_num_leaves(const pk_commitment* c) { return c ? c->L : 0; }
+size_t pk_commit_leaf_width(const pk_commitment* c) { return c ? c->w : 0; }
+
+int pk_commit_open(pk_ctx* ctx, const pk_commitment* c, const uint64_t* sorted_idx, size_t n_idx, uint64_t* leaves_out,
+                   uint64_t* sibling_out, uint64_t* prefix_len_out, uint64_t* suffix_out, uint64_t* suffix_len_out,
+                   size_t suffix_cap) {
+    PK_CHECK(ctx, ctx && c && (n_idx == 0 || (sorted_idx && leaves_out && sibling_out && prefix_len_out && suffix_out && suffix_len_out)),
+             "commit_open: null argument");
+    if (n_idx == 0) return PK_OK;
+    for (size_t i = 0; i < n_idx; i++) {
+        PK_CHECK(ctx, sorted_idx[i] < c->L, "commit_open: index %llu out of range", (unsigned long long)sorted_idx[i]);
+        PK_CHECK(ctx, i == 0 || sorted_idx[i] > sorted_idx[i - 1], "commit_open: indexes must be strictly increasing");
+    }
+    const int depth = c->depth;
+    size_t n_rows = n_idx * c->w, n_path = n_idx * (size_t)depth;
+    PK_TRY(ensure_small(ctx, n_idx * 8));
+    PK_TRY(ensure_tables(ctx, n_rows + n_path));
+    PK_TRY(ensure_stage(ctx, (n_rows + n_path) * 32));
+    PK_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, sorted_idx, n_idx * 8, cudaMemcpyHostToDevice, ctx->stream));
+    char* d_rows = (char*)ctx->d_tables;
+    char* d_path = d_rows + n_rows * 32;
+    ctx->launches += launch_gather_rows(ctx->stream, c->leaves, c->w, (const uint64_t*)ctx->d_small, n_idx, d_rows);
+    ctx->launches += launch_gather_paths(ctx->stream, c->nodes, c->L, (const uint64_t*)ctx->d_small, n_idx, depth, d_path);
+    PK_CUDA(ctx, cudaGetLastError());
+    PK_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage, d_rows, (n_rows + n_path) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::memcpy(leaves_out, ctx->h_stage, n_rows * 32);
+    const uint64_t* paths = (const uint64_t*)((char*)ctx->h_stage + n_rows * 32);
+    // ark MultiPath: sibling leaf digest + auth path root->leaf (excluding the leaf level), prefix-compressed
+    // against the previous path (recursive-verifier/app/circuit/mt.go:36-50, utilities.go:71-82)
+    size_t used = 0;
+    const int plen = depth - 1;
+    for (size_t q = 0; q < n_idx; q++) {
+        const uint64_t* cur = paths + q * depth * 4;
+        std::memcpy(sibling_out + 4 * q, cur, 32);
+        int k = 0;
+        if (q > 0) {
+            const uint64_t* prev = paths + (q - 1) * depth * 4;
+            // root->leaf element j is gathered level depth-1-j
+            while (k < plen && std::memcmp(prev + (size_t)(depth - 1 - k) * 4, cur + (size_t)(depth - 1 - k) * 4, 32) == 0) k++;
+        }
+        prefix_len_out[q] = (uint64_t)k;
+        suffix_len_out[q] = (uint64_t)(plen - k);
+        PK_CHECK(ctx, used + (size_t)(plen - k) <= suffix_cap, "commit_open: suffix_out too small");
+        for (int j = k; j < plen; j++) std::memcpy(suffix_out + 4 * (used++), cur + (size_t)(depth - 1 - j) * 4, 32);
+    }
+    return PK_OK;
+}
+
+// ---- univariate / multilinear helpers ------------------------------------------------------------
+static int split_bits(int n) { return n / 2; }  // low-table bits
+
+int pk_eval_univariate(pk_ctx* ctx, const pk_buf* coeffs, size_t n, const uint64_t z[4], uint64_t out[4]) {
+    PK_CHECK(ctx, coeffs && z && out && n >= 1 && (n & (n - 1)) == 0 && coeffs->n >= n, "eval_univariate: bad arguments");
+    int nv = 0;
+    while (((size_t)1 << nv) < n) nv++;
+    // point (z^(2^(nv-1)), ..., z^2, z) : power tables instead of eq tables
+    std::vector<pkh::Fr> pt(nv > 0 ? nv : 1);
+    pkh::Fr acc;
+    std::memcpy(acc.l, z, 32);
+    for (int i = 0; i < nv; i++) {
+        pt[nv - 1 - i] = acc;
+        acc = pkh::sqr(acc);
+    }
+    int lo = split_bits(nv), hi = nv - lo;
+    PK_TRY(ensure_small(ctx, (size_t)(nv + 1) * 32));
+    PK_TRY(ensure_tables(ctx, ((size_t)1 << lo) + ((size_t)1 << hi)));
+    PK_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, pt.data(), (size_t)nv * 32, cudaMemcpyHostToDevice, ctx->stream));
+    char* t_hi = (char*)ctx->d_tables;
+    char* t_lo = t_hi + ((size_t)32 << hi);
+    ctx->launches += launch_tensor_tables(ctx->stream, ctx->d_small, 1, nv, 0, hi, nullptr, false, t_hi);
+    ctx->launches += launch_tensor_tables(ctx->stream, ctx->d_small, 1, nv, hi, lo, nullptr, false, t_lo);
+    ctx->launches += launch_tensor_dot(ctx->stream, coeffs->d, n, t_hi, t_lo, lo, ctx->d_partials, ctx->d_result);
+    return fetch_result(ctx, out, 1);
+}
+int pk_axpy(pk_ctx* ctx, pk_buf* y, const pk_buf* x, const uint64_t a[4], size_t n) {
+    PK_CHECK(ctx, y && x && a && y->n >= n && x->n >= n, "axpy: buffer too small");
+    ctx->launches += launch_axpy(ctx->stream, y->d, x->d, to_arg(a), n);
+    PK_CUDA(ctx, cudaGetLastError());
+    return PK_OK;
+}
+int pk_dot(pk_ctx* ctx, const pk_buf* a, const pk_buf* b, size_t n, uint64_t out[4]) {
+    PK_CHECK(ctx, a && b && out && a->n >= n && b->n >= n && n >= 1, "dot: buffer too small");
+    ctx->launches += launch_dot(ctx->stream, a->d, b->d, n, ctx->d_partials, ctx->d_result);
+    return fetch_result(ctx, out, 1);
+}
+int pk_eval_eq_batch(pk_ctx* ctx, const uint64_t* points, size_t k, int n, const uint64_t* scalars, pk_buf* out) {
+    PK_CHECK(ctx, points && scalars && out && n >= 0 && n < 40 && out->n >= ((size_t)1 << n), "eval_eq: bad arguments");
+    if (k == 0) return PK_OK;
+    int lo = split_bits(n), hi = n - lo;
+    size_t pts_bytes = k * (size_t)(n > 0 ? n : 1) * 32, sc_bytes = k * 32;
+    PK_TRY(ensure_small(ctx, pts_bytes + sc_bytes));
+    PK_TRY(ensure_tables(ctx, k * (((size_t)1 << lo) + ((size_t)1 << hi))));
+    char* d_pts = (char*)ctx->d_small;
+    char* d_sc = d_pts + pts_bytes;
+    if (n > 0) PK_CUDA(ctx, cudaMemcpyAsync(d_pts, points, k * (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    PK_CUDA(ctx, cudaMemcpyAsync(d_sc, scalars, sc_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    char* t_hi = (char*)ctx->d_tables;
+    char* t_lo = t_hi + k * ((size_t)32 << hi);
+    ctx->launches += launch_tensor_tables(ctx->stream, d_pts, k, n, 0, hi, d_sc, true, t_hi);
+    ctx->launches += launch_tensor_tables(ctx->stream, d_pts, k, n, hi, lo, nullptr, true, t_lo);
+    ctx->launches += launch_tensor_accumulate(ctx->stream, out->d, n, t_hi, t_lo, k, lo);
+    PK_CUDA(ctx, cudaGetLastError());
+    // the host arrays may be reused by the caller right away
+    PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PK_OK;
+}
+int pk_eval_eq(pk_ctx* ctx, const uint64_t* point, int n, const uint64_t scalar[4], pk_buf* out) {
+    return pk_eval_eq_batch(ctx, point, 1, n, scalar, out);
+}
+int pk_mle_eval(pk_ctx* ctx, const pk_buf* evals, int log_n, const uint64_t* point, uint64_t out[4]) {
+    PK_CHECK(ctx, evals && point && out && log_n >= 0 && log_n < 40 && evals->n >= ((size_t)1 << log_n), "mle_eval: bad arguments");
+    int lo = split_bits(log_n), hi = log_n - lo;
+    PK_TRY(ensure_small(ctx, (size_t)(log_n + 1) * 32));
+    PK_TRY(ensure_tables(ctx, ((size_t)1 << lo) + ((size_t)1 << hi)));
+    if (log_n > 0) PK_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, point, (size_t)log_n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    char* t_hi = (char*)ctx->d_tables;
+    char* t_lo = t_hi + ((size_t)32 << hi);
+    ctx->launches += launch_tensor_tables(ctx->stream, ctx->d_small, 1, log_n, 0, hi, nullptr, true, t_hi);
+    ctx->launches += launch_tensor_tables(ctx->stream, ctx->d_small, 1, log_n, hi, lo, nullptr, true, t_lo);
+    ctx->launches += launch_tensor_dot(ctx->stream, evals->d, (size_t)1 << log_n, t_hi, t_lo, lo, ctx->d_partials, ctx->d_result);
+    return fetch_result(ctx, out, 1);
+}
+int pk_fold_coeffs(pk_ctx* ctx, const pk_buf* coeffs, int log_n, const uint64_t* r, int k, pk_buf* out) {
+    PK_CHECK(ctx, coeffs && r && out && k >= 0 && k <= 4 && log_n >= k && log_n < 40, "fold_coeffs: bad arguments");
+    PK_CHECK(ctx, coeffs->n >= ((size_t)1 << log_n) && out->n >= ((size_t)1 << (log_n - k)), "fold_coeffs: buffer too small");
+    PK_TRY(ensure_small(ctx, 4 * 32));
+    if (k > 0) PK_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, r, (size_t)k * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->launches += launch_fold_coeffs(ctx->stream, coeffs->d, log_n, ctx->d_small, k, out->d);
+    PK_CUDA(ctx, cudaGetLastError());
+    PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PK_OK;
+}
+
+// ---- sumchecks -----------------------------------------------------------------------------------
+int pk_zk_sumcheck_round(pk_ctx* ctx, pk_buf* a, pk_buf* b, pk_buf* c, pk_buf* eq, int log_n, const uint64_t* fold,
+                         uint64_t out3[12]) {
+    PK_CHECK(ctx, a && b && c && eq && out3, "zk_sumcheck_round: null argument");
+    // sumcheck.rs:21-24: power of two, >= 2, equal lengths; :27: >= 4 when folding
+    PK_CHECK(ctx, log_n >= (fold ? 2 : 1) && log_n < 40, "zk_sumcheck_round: size must be >= %d", fold ? 4 : 2);
+    size_t n = (size_t)1 << log_n;
+    PK_CHECK(ctx, a->n >= n && b->n >= n && c->n >= n && eq->n >= n, "zk_sumcheck_round: arrays shorter than 2^log_n");
+    fr_arg f = {};
+    if (fold) f = to_arg(fold);
+    ctx->launches += launch_zk_sumcheck_round(ctx->stream, a->d, b->d, c->d, eq->d, log_n, fold != nullptr, f, ctx->d_partials,
+                                              ctx->d_result);
+    return fetch_result(ctx, out3, 3);
+}
+int pk_whir_sumcheck_round(pk_ctx* ctx, const pk_buf* p_in, const pk_buf* w_in, pk_buf* p_out, pk_buf* w_out, int log_n,
+                           const uint64_t* fold, uint64_t out3[12]) {
+    PK_CHECK(ctx, p_in && w_in && out3, "whir_sumcheck_round: null argument");
+    PK_CHECK(ctx, log_n >= (fold ? 2 : 1) && log_n < 40, "whir_sumcheck_round: size must be >= %d", fold ? 4 : 2);
+    size_t n = (size_t)1 << log_n;
+    PK_CHECK(ctx, p_in->n >= n && w_in->n >= n, "whir_sumcheck_round: inputs shorter than 2^log_n");
+    fr_arg f = {};
+    if (fold) {
+        PK_CHECK(ctx, p_out && w_out && p_out->n >= n / 2 && w_out->n >= n / 2, "whir_sumcheck_round: outputs too small");
+        PK_CHECK(ctx, p_out->d != p_in->d && w_out->d != w_in->d, "whir_sumcheck_round: folding needs distinct output buffers");
+        f = to_arg(fold);
+    }
+    ctx->launches += launch_whir_sumcheck_round(ctx->stream, p_in->d, w_in->d, fold ? p_out->d : nullptr, fold ? w_out->d : nullptr,
+                                                log_n, fold != nullptr, f, ctx->d_partials, ctx->d_result);
+    return fetch_result(ctx, out3, 3);
+}
+
+// ---- measurement helper (not part of the reference surface) ----------------------------------------
+int pk_modmul_bench(pk_ctx* ctx, size_t n_threads, int iters, float* ms_out) {
+    PK_CHECK(ctx, ctx && ms_out && n_threads % 256 == 0 && n_threads > 0, "modmul_bench: n_threads must be a multiple of 256");
+    PK_TRY(ensure_scratch(ctx, 2 * n_threads));
+    PK_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0x11, 2 * n_threads * 32, ctx->stream));
+    ctx->launches += launch_to_mont(ctx->stream, ctx->d_scratch, 2 * n_threads, true);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    launch_modmul_bench(ctx->stream, ctx->d_scratch, n_threads, 8);  // warm-up
+    cudaEventRecord(e0, ctx->stream);
+    ctx->launches += launch_modmul_bench(ctx->stream, ctx->d_scratch, n_threads, iters);
+    cudaEventRecord(e1, ctx->stream);
+    PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(ms_out, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return PK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// provekit_b200/csrc/skyscraper.cuh — Skyscraper-v2 two-to-one compression on the B200 integer pipe.
+//
+// Replaces skyscraper::simple::compress (skyscraper/core/src/simple.rs:12-14 -> generic.rs:77-102) as
+// called by the Merkle plug-in (provekit/common/src/skyscraper/whir.rs:20-25) and the PoW solver
+// (skyscraper/core/src/generic.rs:42-71).  Spec: skyscraper/core/src/reference.rs:41-98.
+// 18 Feistel rounds (l, r) <- (r + F_i(l) + rc_i, l); F = x^2 * 2^-256 (a raw Montgomery square, the
+// block_multiplier::scalar_sqr semantics) except rounds 6,7,10,11 where F = bar.  All values are raw
+// canonical integers in [0, p); the reference keeps lazily reduced representatives, which only `bar`
+// could observe and it canonicalises first (bar.rs:17), so outputs are bit-identical.
+#pragma once
+#include "fr.cuh"
+
+namespace pk {
+
+// skyscraper/core/src/constants.rs:32-51 as 32-bit little-endian limbs
+__constant__ uint32_t SKY_RC[18][8] = {
+    {0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u},
+    {0x270bd744u, 0x903c4324u, 0x08a7d269u, 0x873125f7u, 0x06c83855u, 0x081dd279u, 0xea6d7667u, 0x276b1823u},
+    {0x4b378d71u, 0x7ac8edbbu, 0xd99e2cb7u, 0xe29d79f3u, 0x4c1a5a18u, 0x75141791u, 0x58a484a6u, 0x0cf02bd7u},
+    {0x69e5bc36u, 0xfa7adc67u, 0x7cca387du, 0x1c3f8e29u, 0x63481db0u, 0x0eb7730du, 0x18ede544u, 0x25b0e03fu},
+    {0x2f03cfb7u, 0x57847e65u, 0x68873404u, 0x33440b96u, 0x49af80bcu, 0x955a32e8u, 0xbe14ae70u, 0x002882fcu},
+    {0x6257d4d7u, 0x97923139u, 0x1b37d3c1u, 0x29989c3eu, 0x7f1277bau, 0x12ef02b4u, 0x1e2b7a9cu, 0x039ad857u},
+    {0xabbb7887u, 0xb5b48465u, 0xe6ba2d2bu, 0xa72a6bc5u, 0x712f7b29u, 0x4cd48043u, 0x0fc1fc1au, 0x1142d541u},
+    {0x059075d3u, 0x7ab2c156u, 0x047999b2u, 0x17cb3594u, 0x98f289f7u, 0x44f2c935u, 0x69bc0becu, 0x1d78439fu},
+    {0x138b8edbu, 0x05d7a965u, 0xd55c48b1u, 0x36ef35a3u, 0xac6f1628u, 0x8ddfb8a1u, 0x08f4ff82u, 0x258588a5u},
+    {0xfccb49e9u, 0x1596fb9au, 0x9a09a95bu, 0x9a7367d6u, 0x84e4c157u, 0x9bc43f69u, 0xd2f514feu, 0x13087879u},
+    {0x3b4109fau, 0x295ccd23u, 0xed868012u, 0xe1d72f89u, 0x4bc88a8eu, 0x2e9e1eeau, 0x98c45232u, 0x17dadee8u},
+    {0xaa1f486fu, 0x9a8590b4u, 0x30e9130eu, 0xb75834b4u, 0x34d5de31u, 0xb8e90b10u, 0x46e7f4a6u, 0x295c6d15u},
+    {0x4c6eb892u, 0x850adcb7u, 0x05b92fc3u, 0x07699ef3u, 0xa1720f2du, 0x4ef96a2bu, 0x1d3ed446u, 0x1288ca0eu},
+    {0x49d1b5eeu, 0x01960f93u, 0x69371c69u, 0x8ccad307u, 0x91c98662u, 0xe5c81e89u, 0x1ae023f3u, 0x17563b4du},
+    {0x76b32917u, 0x6ba01e94u, 0xdd977bc9u, 0xa1cb0a3au, 0x5815f030u, 0x86815a94u, 0xe91a1eeau, 0x2869043bu},
+    {0x5511d976u, 0x81776c88u, 0x47f414e7u, 0x7475d34fu, 0x095d96cfu, 0x5d090056u, 0xff59e79au, 0x14941f0au},
+    {0x8fc8c034u, 0xbc40b4fdu, 0xcce4fd48u, 0xbb7142c3u, 0x8a39005au, 0x31835675u, 0x90f4379fu, 0x1ce337a1u},
+    {0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u},
+};
+
+// per-byte sbox on 4 packed bytes (bar.rs:40-65): rotl1(v ^ (~rotl1(v) & rotl2(v) & rotl3(v)))
+__device__ __forceinline__ uint32_t sbox4(uint32_t v) {
+    uint32_t t1 = ((v & 0x80808080u) >> 7) | ((v & 0x7f7f7f7fu) << 1);
+    uint32_t t2 = ((v & 0xc0c0c0c0u) >> 6) | ((v & 0x3f3f3f3fu) << 2);
+    uint32_t t3 = ((v & 0xe0e0e0e0u) >> 5) | ((v & 0x1f1f1f1fu) << 3);
+    uint32_t tmp = (~t1 & t2 & t3) ^ v;
+    return ((tmp & 0x80808080u) >> 7) | ((tmp & 0x7f7f7f7fu) << 1);
+}
+
+// value < 2^256 -> [0, p): q = floor(top limb / (P7+1)) in 0..5, subtract q*p, one conditional subtract
+// (the reduce_partial idea of skyscraper/core/src/reduce.rs:33-40 followed by reduce_1 :21-29)
+__device__ __forceinline__ fr sky_reduce(const fr& x) {
+    uint32_t q = x.v[7] / (PK_P7 + 1u);
+    uint32_t qp[8];
+    uint32_t c;
+    // q*p: q <= 5 so every product fits well inside 64 bits; one chain of wide multiplies
+    asm("{\n\t"
+        ".reg .u32 hi;\n\t"
+        "mul.lo.u32 %0, %9, %10;\n\t"
+        "mul.hi.u32 hi, %9, %10;\n\t"
+        "mad.lo.cc.u32 %1, %9, %11, hi;\n\t"
+        "madc.hi.u32 hi, %9, %11, 0;\n\t"
+        "mad.lo.cc.u32 %2, %9, %12, hi;\n\t"
+        "madc.hi.u32 hi, %9, %12, 0;\n\t"
+        "mad.lo.cc.u32 %3, %9, %13, hi;\n\t"
+        "madc.hi.u32 hi, %9, %13, 0;\n\t"
+        "mad.lo.cc.u32 %4, %9, %14, hi;\n\t"
+        "madc.hi.u32 hi, %9, %14, 0;\n\t"
+        "mad.lo.cc.u32 %5, %9, %15, hi;\n\t"
+        "madc.hi.u32 hi, %9, %15, 0;\n\t"
+        "mad.lo.cc.u32 %6, %9, %16, hi;\n\t"
+        "madc.hi.u32 hi, %9, %16, 0;\n\t"
+        "mad.lo.cc.u32 %7, %9, %17, hi;\n\t"
+        "madc.hi.u32 %8, %9, %17, 0;\n\t"
+        "}"
+        : "=r"(qp[0]), "=r"(qp[1]), "=r"(qp[2]), "=r"(qp[3]), "=r"(qp[4]), "=r"(qp[5]), "=r"(qp[6]), "=r"(qp[7]),
+          "=r"(c)
+        : "r"(q), "r"(PK_P0), "r"(PK_P1), "r"(PK_P2), "r"(PK_P3), "r"(PK_P4), "r"(PK_P5), "r"(PK_P6), "r"(PK_P7));
+    fr d;
+    asm("sub.cc.u32 %0, %8, %16;\n\t"
+        "subc.cc.u32 %1, %9, %17;\n\t"
+        "subc.cc.u32 %2, %10, %18;\n\t"
+        "subc.cc.u32 %3, %11, %19;\n\t"
+        "subc.cc.u32 %4, %12, %20;\n\t"
+        "subc.cc.u32 %5, %13, %21;\n\t"
+        "subc.cc.u32 %6, %14, %22;\n\t"
+        "subc.u32 %7, %15, %23;"
+        : "=r"(d.v[0]), "=r"(d.v[1]), "=r"(d.v[2]), "=r"(d.v[3]), "=r"(d.v[4]), "=r"(d.v[5]), "=r"(d.v[6]),
+          "=r"(d.v[7])
+        : "r"(x.v[0]), "r"(x.v[1]), "r"(x.v[2]), "r"(x.v[3]), "r"(x.v[4]), "r"(x.v[5]), "r"(x.v[6]), "r"(x.v[7]),
+          "r"(qp[0]), "r"(qp[1]), "r"(qp[2]), "r"(qp[3]), "r"(qp[4]), "r"(qp[5]), "r"(qp[6]), "r"(qp[7]));
+    return fr_reduce_once(d);
+}
+
+// bar on a canonical value: swap the 16-byte halves, sbox every byte, reduce (reference.rs:80-94)
+__device__ __forceinline__ fr sky_bar(const fr& x) {
+    fr y;
+    y.v[0] = sbox4(x.v[4]); y.v[1] = sbox4(x.v[5]); y.v[2] = sbox4(x.v[6]); y.v[3] = sbox4(x.v[7]);
+    y.v[4] = sbox4(x.v[0]); y.v[5] = sbox4(x.v[1]); y.v[6] = sbox4(x.v[2]); y.v[7] = sbox4(x.v[3]);
+    return sky_reduce(y);
+}
+
+__device__ __forceinline__ fr sky_rc(int i) {
+    fr c;
+#pragma unroll
+    for (int k = 0; k < 8; k++) c.v[k] = SKY_RC[i][k];
+    return c;
+}
+
+// l, r canonical (< p).  Returns compress(l, r) canonical.
+__device__ __forceinline__ fr sky_compress(const fr& l_in, const fr& r_in) {
+    fr l = l_in, r = r_in;
+#pragma unroll 1
+    for (int i = 0; i < 18; i++) {
+        bool is_bar = (i == 6) | (i == 7) | (i == 10) | (i == 11);
+        fr f = is_bar ? sky_bar(l) : fr_mul(l, l);
+        fr nl = fr_add(fr_add(r, f), sky_rc(i));
+        r = l;
+        l = nl;
+    }
+    return fr_add(l, l_in);
+}
+
+// provekit/common/src/skyscraper/whir.rs:20-25 on Montgomery-form field elements
+__device__ __forceinline__ fr sky_compress_mont(const fr& l, const fr& r) {
+    return fr_to_mont(sky_compress(fr_from_mont(l), fr_from_mont(r)));
+}
+
+}  // namespace pk

@@ -1,0 +1,303 @@
+"""GPU parity: every sm_100a kernel, called through the C-ABI (libpkwhir.so), against the CPU oracle on
+the same seeded inputs — bit-exact (integer arithmetic).  Run on the B200 box: pytest -m gpu."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from helpers import arr_to_ints, from_mont, ints_to_arr, ptr, rand_fr, to_mont
+from oracle import pyref as o
+
+pytestmark = pytest.mark.gpu
+P = o.P
+sz = ctypes.c_size_t
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import provekit_b200 as pk
+    c = pk.Context(0)
+    yield c
+    c.close()
+
+
+def rng_fr(seed, n):
+    return rand_fr(np.random.default_rng(seed), n)
+
+
+# ---- Skyscraper ------------------------------------------------------------------------------------
+def test_compress_many_kats(ctx):
+    """reference.rs:153-188 KATs through the CompressManyFn seam: compress = permute(l,r).0 + l."""
+    cases = [(0, 0), (50417215636675310123686652273432694184389644587803328798109154235492038730484,
+                      14620920779025509970947930308416120371903474543120179490887326852503500806990)]
+    exp_l = [5793276905781313965269111743763131906666794041798623267477617572701829069290,
+             8412949970293910117511617126618515787729842528183672400383899220234743146062]
+    msgs = b"".join(l.to_bytes(32, "little") + r.to_bytes(32, "little") for l, r in cases)
+    out = ctx.compress_many(msgs)
+    for i, (l, _) in enumerate(cases):
+        assert int.from_bytes(out[32 * i:32 * i + 32], "little") == (exp_l[i] + l) % P
+
+
+@pytest.mark.parametrize("n", [1, 3, 128, 1000, 70001])
+def test_compress_many_vs_oracle(ctx, orc, n):
+    rng = np.random.default_rng(n)
+    msgs = rng.integers(0, 1 << 64, size=(n, 8), dtype=np.uint64)  # arbitrary 256-bit values (>= p allowed)
+    edge = [0, (1 << 256) - 1, P - 1, P, 2 * P, P + 1, 5 * P, 5 * P + 12345, 1 << 255]
+    for i, e in enumerate(edge[:n]):
+        msgs[i, :4] = ints_to_arr([e])[0]
+        msgs[i, 4:] = ints_to_arr([edge[-1 - i]])[0]
+    exp = np.zeros((n, 4), np.uint64)
+    orc.orc_sky_compress_many(ptr(msgs), ptr(exp), sz(n), 2)
+    assert ctx.compress_many(msgs.tobytes()) == exp.tobytes()
+
+
+def test_compress_many_empty_and_ragged(ctx):
+    assert ctx.compress_many(b"") == b""
+    with pytest.raises(ValueError):
+        ctx.compress_many(b"\0" * 65)  # generic.rs:19 "Message length not a multiple of 64"
+
+
+@pytest.mark.parametrize("bits", [0.0, 3.141592653589793, 10.0, 17.5])
+def test_pow_solve_vs_oracle(ctx, orc, bits):
+    for ch in ([(1 << 64) - 1] * 4, [5, 6, 7, 8]):  # pow.rs:105-111 uses challenge = [u64::MAX; 4]
+        cha = np.array(ch, dtype=np.uint64)
+        nonce = ctx.pow_solve(cha, bits)
+        assert nonce == orc.orc_pow_solve(ptr(cha), bits)
+        assert orc.orc_pow_verify(ptr(cha), bits, ctypes.c_uint64(nonce)) == 1
+
+
+def test_pow_bits_out_of_range(ctx):
+    from provekit_b200 import PkError
+    with pytest.raises(PkError):
+        ctx.pow_solve(np.zeros(4, np.uint64), 60.0)  # provekit/common/src/skyscraper/pow.rs:16
+
+
+# ---- wavelet / RS encode -----------------------------------------------------------------------------
+@pytest.mark.parametrize("log_n", [0, 1, 4, 11, 12, 16, 19])
+def test_wavelet_vs_oracle(ctx, orc, log_n):
+    a = rng_fr(log_n, 1 << log_n)
+    exp = a.copy()
+    orc.orc_evals_to_coeffs(ptr(exp), log_n)
+    buf = ctx.upload(a)
+    ctx.evals_to_coeffs(buf, log_n)
+    got = buf.download()
+    assert np.array_equal(got, exp)
+    ctx.coeffs_to_evals(buf, log_n)
+    assert np.array_equal(buf.download(), a)  # round trip
+    buf.free()
+
+
+@pytest.mark.parametrize("log_n,rate", [(4, 1), (4, 4), (5, 13), (9, 10), (11, 1), (12, 2), (13, 7), (17, 4), (18, 1), (20, 1)])
+def test_rs_encode_vs_oracle(ctx, orc, log_n, rate):
+    a = rng_fr(1000 + log_n, 1 << log_n)
+    rows = 1 << (log_n + rate - 4)
+    exp = np.zeros((rows * 16, 4), np.uint64)
+    orc.orc_rs_encode(ptr(a), log_n, rate, 4, ptr(exp), sz(16), sz(0))
+    coeffs = ctx.upload(a)
+    leaves = ctx.buffer(rows * 16)
+    ctx.rs_encode(coeffs, log_n, rate, leaves)
+    assert np.array_equal(leaves.download(), exp)
+    coeffs.free()
+    leaves.free()
+
+
+def test_rs_encode_reference_proof_kat(ctx):
+    """SURVEY A.6 on the GPU: RS-encode the 32 coefficients recovered from the reference-produced proof
+    and compare the 9 opened leaves byte for byte."""
+    import fixture_walk as fw
+    w = fw.walk_proof()["whir_w"]
+    leaves, idx = w["final_answers"], w["final_multipath"][3]
+    g16 = pow(o.root_of_unity(18), 16, P)
+    y = [pow(g16, i, P) for i in idx]
+    inv = pow((y[1] - y[0]) % P, -1, P)
+    hi = [(leaves[1][k] - leaves[0][k]) * inv % P for k in range(16)]
+    lo = [(leaves[0][k] - hi[k] * y[0]) % P for k in range(16)]
+    coeffs = ctx.upload(to_mont(lo + hi))
+    out = ctx.buffer((1 << 14) * 16)
+    ctx.rs_encode(coeffs, 5, 13, out)
+    got = out.download()
+    for i, leaf in zip(idx, leaves):
+        assert from_mont(got[i * 16:(i + 1) * 16]) == leaf
+
+
+# ---- Merkle / commit / open ----------------------------------------------------------------------------
+@pytest.mark.parametrize("L,w", [(2, 16), (8, 32), (512, 16), (1024, 32), (4096, 1), (1 << 14, 16)])
+def test_merkle_vs_oracle(ctx, orc, L, w):
+    a = rng_fr(L + w, L * w)
+    exp = np.zeros((2 * L, 4), np.uint64)
+    orc.orc_merkle_build(ptr(a), sz(L), sz(w), ptr(exp), 2)
+    exp_canon = np.zeros_like(exp)
+    orc.orc_from_montgomery(ptr(exp), ptr(exp_canon), sz(2 * L))
+    leaves, nodes = ctx.upload(a), ctx.buffer(2 * L)
+    ctx.merkle_build(leaves, L, w, nodes)
+    got = nodes.download()
+    assert np.array_equal(got[1:], exp_canon[1:])
+    leaves.free()
+    nodes.free()
+
+
+def test_merkle_errors(ctx):
+    from provekit_b200 import PkError
+    leaves, nodes = ctx.buffer(64), ctx.buffer(16)
+    with pytest.raises(PkError) as e:
+        ctx.merkle_build(leaves, 4, 0, nodes)  # empty leaf: IncorrectInputLength(0), skyscraper/whir.rs:47
+    assert e.value.code == -6
+    with pytest.raises(PkError):
+        ctx.merkle_build(leaves, 3, 16, nodes)
+
+
+@pytest.mark.parametrize("log_n,rate,batch", [(8, 1, 2), (12, 1, 2), (13, 4, 1), (16, 1, 2)])
+def test_commit_batch_and_open(ctx, orc, log_n, rate, batch):
+    polys = [rng_fr(7 * log_n + b, 1 << log_n) for b in range(batch)]
+    L = 1 << (log_n + rate - 4)
+    w = 16 * batch
+    leaves = np.zeros((L * w, 4), np.uint64)
+    for b in range(batch):
+        orc.orc_rs_encode(ptr(polys[b]), log_n, rate, 4, ptr(leaves), sz(w), sz(16 * b))
+    nodes = np.zeros((2 * L, 4), np.uint64)
+    orc.orc_merkle_build(ptr(leaves), sz(L), sz(w), ptr(nodes), 2)
+    bufs = [ctx.upload(p) for p in polys]
+    cm = ctx.commit_batch(bufs, log_n, rate)
+    assert (cm.num_leaves, cm.leaf_width) == (L, w)
+    assert np.array_equal(cm.root, nodes[1])  # Montgomery root
+    rng = np.random.default_rng(log_n)
+    idx = sorted(set(int(i) for i in rng.integers(0, L, size=40)) | {0, L - 1})
+    got_leaves, sib, pre, sufs = cm.open(idx)
+    nodes_int = from_mont(nodes)
+    e_sib, e_pre, e_suf, _ = o.merkle_multipath(nodes_int, idx)
+    assert arr_to_ints(sib) == e_sib
+    assert [int(x) for x in pre] == e_pre
+    assert [arr_to_ints(s) if len(s) else [] for s in sufs] == e_suf
+    lv = leaves.reshape(L, w, 4)
+    for j, i in enumerate(idx):
+        assert np.array_equal(got_leaves[j], lv[i])
+    # and the opened paths verify against the root like the Go verifier does (whir_utilities.go:13-46)
+    prev = []
+    root = nodes_int[1]
+    for j, i in enumerate(idx[:5]):
+        prev = prev[:e_pre[j]] + e_suf[j]
+        assert o.merkle_verify_path(root, i, from_mont(got_leaves[j]), e_sib[j], prev)
+    cm.free()
+    for b in bufs:
+        b.free()
+
+
+def test_commit_open_rejects_unsorted(ctx):
+    from provekit_b200 import PkError
+    b = ctx.upload(rng_fr(1, 256))
+    cm = ctx.commit_batch([b], 8, 1)
+    with pytest.raises(PkError):
+        cm.open([3, 3])
+    with pytest.raises(PkError):
+        cm.open([cm.num_leaves])
+    cm.free()
+    b.free()
+
+
+# ---- helpers -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("log_n", [0, 1, 5, 13, 18])
+def test_univariate_dot_axpy_fold_mle(ctx, orc, log_n):
+    n = 1 << log_n
+    a, b = rng_fr(log_n, n), rng_fr(log_n + 50, n)
+    z = rng_fr(99, 1)
+    exp = np.zeros(4, np.uint64)
+    da, db = ctx.upload(a), ctx.upload(b)
+    orc.orc_eval_univariate(ptr(a), sz(n), ptr(z), ptr(exp))
+    assert np.array_equal(ctx.eval_univariate(da, n, z), exp)
+    orc.orc_dot(ptr(a), ptr(b), sz(n), ptr(exp))
+    assert np.array_equal(ctx.dot(da, db, n), exp)
+    pt = rng_fr(7, max(log_n, 1))[:log_n]
+    orc.orc_mle_eval(ptr(a), log_n, ptr(pt), ptr(exp))
+    assert np.array_equal(ctx.mle_eval(da, log_n, pt), exp)
+    if log_n >= 4:
+        r = rng_fr(8, 4)
+        ef = np.zeros((n // 16, 4), np.uint64)
+        orc.orc_fold_coeffs(ptr(a), log_n, ptr(r), 4, ptr(ef))
+        out = ctx.buffer(n // 16)
+        ctx.fold_coeffs(da, log_n, r, out)
+        assert np.array_equal(out.download(), ef)
+        out.free()
+    ea = a.copy()
+    orc.orc_axpy(ptr(ea), ptr(b), ptr(z), sz(n))
+    ctx.axpy(da, db, z, n)
+    assert np.array_equal(da.download(), ea)
+    da.free()
+    db.free()
+
+
+@pytest.mark.parametrize("n,k", [(0, 1), (1, 2), (4, 3), (9, 29), (13, 110), (17, 5)])
+def test_eval_eq_batch(ctx, orc, n, k):
+    N = 1 << n
+    base = rng_fr(n + k, N)
+    pts = rng_fr(3 * n + 1, max(k * n, 1))[:k * n]
+    sc = rng_fr(5, k)
+    exp = base.copy()
+    for j in range(k):
+        orc.orc_eval_eq_accumulate(ptr(np.ascontiguousarray(pts[j * n:(j + 1) * n])), n, ptr(np.ascontiguousarray(sc[j])), ptr(exp))
+    out = ctx.upload(base)
+    ctx.eval_eq(pts, sc, n, out)
+    assert np.array_equal(out.download(), exp)
+    out.free()
+
+
+# ---- sumchecks ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("log_n", [1, 2, 3, 8, 15, 19])
+def test_zk_sumcheck_all_rounds(ctx, orc, log_n):
+    n = 1 << log_n
+    host = [rng_fr(10 * log_n + k, n) for k in range(4)]
+    dev = [ctx.upload(h) for h in host]
+    fold = None
+    cur = log_n
+    for rnd in range(log_n):
+        exp = np.zeros((3, 4), np.uint64)
+        orc.orc_zk_sumcheck_round(ptr(host[0]), ptr(host[1]), ptr(host[2]), ptr(host[3]), cur, ptr(fold) if fold is not None else None, ptr(exp))
+        got = ctx.sumcheck_fold_map_reduce(*dev, cur, fold)
+        assert np.array_equal(got, exp), f"round {rnd}"
+        if fold is not None:
+            cur -= 1
+        if rnd in (1, log_n - 1):
+            for k in range(4):
+                assert np.array_equal(dev[k].download(1 << cur), host[k][:1 << cur])
+        fold = rng_fr(1000 + rnd, 1)
+    for d in dev:
+        d.free()
+
+
+def test_zk_sumcheck_asserts(ctx):
+    from provekit_b200 import PkError
+    bufs = [ctx.buffer(4) for _ in range(4)]
+    with pytest.raises(PkError):
+        ctx.sumcheck_fold_map_reduce(*bufs, 0, None)            # sumcheck.rs:23 size >= 2
+    with pytest.raises(PkError):
+        ctx.sumcheck_fold_map_reduce(*bufs, 1, rng_fr(1, 1))    # sumcheck.rs:27 size >= 4 when folding
+    with pytest.raises(PkError):
+        ctx.sumcheck_fold_map_reduce(*bufs, 3, None)            # arrays shorter than 2^log_n
+    for b in bufs:
+        b.free()
+
+
+@pytest.mark.parametrize("log_n", [1, 2, 5, 12, 19])
+def test_whir_sumcheck_all_rounds(ctx, orc, log_n):
+    n = 1 << log_n
+    hp, hw = rng_fr(log_n, n), rng_fr(log_n + 77, n)
+    bufs = [(ctx.upload(hp), ctx.upload(hw)), (ctx.buffer(max(n // 2, 1)), ctx.buffer(max(n // 2, 1)))]
+    fold = None
+    cur, which = log_n, 0
+    for rnd in range(log_n):
+        exp = np.zeros((3, 4), np.uint64)
+        orc.orc_whir_sumcheck_round(ptr(hp), ptr(hw), cur, ptr(fold) if fold is not None else None, ptr(exp))
+        src, dst = bufs[which], bufs[1 - which]
+        if fold is None:
+            got = ctx.whir_sumcheck_round(src[0], src[1], cur)
+        else:
+            got = ctx.whir_sumcheck_round(src[0], src[1], cur, fold, dst[0], dst[1])
+            which = 1 - which
+            cur -= 1
+        assert np.array_equal(got, exp), f"round {rnd}"
+        if rnd == log_n - 1 or rnd == 1:
+            assert np.array_equal(bufs[which][0].download(1 << cur), hp[:1 << cur])
+            assert np.array_equal(bufs[which][1].download(1 << cur), hw[:1 << cur])
+        fold = rng_fr(2000 + rnd, 1)
+    for a, b in bufs:
+        a.free()
+        b.free()
