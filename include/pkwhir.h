@@ -169,8 +169,9 @@ void pk_prover_destroy(pk_prover *p);
 /* returns the spongefish NARG string (= WhirR1CSProof.transcript); *out is malloc'd, free with pk_free */
 int pk_prove(pk_prover *p, const uint64_t *witness, const pk_rand *rnd, uint8_t **out, size_t *out_len);
 void pk_free(void *p);
-/* seconds spent per stage in the last pk_prove: [commit_ntt, commit_merkle, zk_sumcheck, whir_sumcheck,
- * pow, open, spmv_weights, other, total] */
+/* host wall-clock seconds per stage of the last pk_prove: [0] witness commit (NTT+Merkle), [1] unused,
+ * [2] zk-sumcheck, [3] WHIR sumcheck rounds, [4] PoW, [5] STIR openings, [6] R1CS mat-vec + weights,
+ * [7] everything else, [8] total */
 void pk_prover_timings(const pk_prover *p, double out[9]);
 
 /* ---- measurement helper (no reference counterpart): `iters` dependent Montgomery multiplications

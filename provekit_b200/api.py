@@ -212,3 +212,48 @@ class Context:
         ms = c_float()
         self._chk(self.L.pk_modmul_bench(self.h, n_threads, iters, byref(ms)))
         return ms.value
+
+
+class Prover:
+    """WhirR1CSProver::prove (provekit/prover/src/whir_r1cs.rs:42-100) over a device-resident R1CS.
+    `r1cs` is a dict with num_constraints, num_witnesses, interned (k,4) and a/b/c = (row_start u64,
+    col u32, val u32) in the reference's interned-CSR form (provekit/common/src/sparse_matrix.rs:19-26)."""
+
+    def __init__(self, ctx: Context, r1cs: dict):
+        self.ctx = ctx
+        self._keep = []
+
+        def csr(t):
+            rs, col, val = (np.ascontiguousarray(t[0], np.uint64), np.ascontiguousarray(t[1], np.uint32),
+                            np.ascontiguousarray(t[2], np.uint32))
+            self._keep += [rs, col, val]
+            return _abi.CSR(r1cs["num_constraints"], r1cs["num_witnesses"], len(col), rs.ctypes.data, col.ctypes.data,
+                            val.ctypes.data)
+
+        interned = _fe(r1cs["interned"])
+        self._keep.append(interned)
+        s = _abi.R1CS(r1cs["num_constraints"], r1cs["num_witnesses"], len(interned), interned.ctypes.data,
+                      csr(r1cs["a"]), csr(r1cs["b"]), csr(r1cs["c"]))
+        h = c_void_p()
+        ctx._chk(ctx.L.pk_prover_create(ctx.h, byref(s), byref(h)))
+        self.h = h
+
+    def prove(self, witness, rand: dict) -> bytes:
+        w = _fe(witness)
+        arrs = [_fe(rand[k]) for k in ("mask_w", "g_w", "blind", "mask_h", "g_h")]
+        rs = _abi.Rand(*[a.ctypes.data for a in arrs])
+        out, n = c_void_p(), c_size_t()
+        self.ctx._chk(self.ctx.L.pk_prove(self.h, _p(w), byref(rs), byref(out), byref(n)))
+        data = ctypes.string_at(out, n.value)
+        self.ctx.L.pk_free(out)
+        return data
+
+    def timings(self):
+        t = (c_double * 9)()
+        self.ctx.L.pk_prover_timings(self.h, t)
+        return list(t)
+
+    def close(self):
+        if self.h:
+            self.ctx.L.pk_prover_destroy(self.h)
+            self.h = None

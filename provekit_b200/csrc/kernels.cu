@@ -569,6 +569,36 @@ int launch_whir_sumcheck_round(cudaStream_t st, const void* p_in, const void* w_
 }
 
 // ------------------------------------------------------------------------------------------------
+// R1CS sparse mat-vec (one thread per row; rows hold 1-3 entries in practice)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_spmv(const uint64_t* __restrict__ row_start, const uint32_t* __restrict__ col,
+                                              const uint32_t* __restrict__ val, const fr* __restrict__ interned,
+                                              const fr* __restrict__ x, fr* out, size_t num_rows, size_t nnz) {
+    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= num_rows) return;
+    size_t s = row_start[r], e = r + 1 < num_rows ? row_start[r + 1] : nnz;
+    fr acc = fr_zero();
+    for (size_t k = s; k < e; k++) acc = fr_add(acc, fr_mul(fr_load_nc(&interned[val[k]]), fr_load_nc(&x[col[k]])));
+    fr_store(&out[r], acc);
+}
+int launch_spmv(cudaStream_t st, const uint64_t* row_start, const uint32_t* col, const uint32_t* val,
+                const void* interned, const void* x, void* out, size_t num_rows, size_t nnz) {
+    if (num_rows == 0) return 0;
+    k_spmv<<<(unsigned)((num_rows + 255) / 256), 256, 0, st>>>(row_start, col, val, (const fr*)interned, (const fr*)x,
+                                                             (fr*)out, num_rows, nnz);
+    return 1;
+}
+__global__ void __launch_bounds__(256) k_mul(const fr* __restrict__ a, const fr* __restrict__ b, fr* out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fr_store(&out[i], fr_mul(fr_load_nc(&a[i]), fr_load_nc(&b[i])));
+}
+int launch_mul(cudaStream_t st, const void* a, const void* b, void* out, size_t n) {
+    if (n == 0) return 0;
+    k_mul<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const fr*)a, (const fr*)b, (fr*)out, n);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K10 gathers for STIR answers / Merkle multipaths
 // ------------------------------------------------------------------------------------------------
 __global__ void k_gather_rows(const fr* __restrict__ leaves, size_t w, const uint64_t* __restrict__ idx, size_t n_idx,

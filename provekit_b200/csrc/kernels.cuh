@@ -54,6 +54,12 @@ int launch_zk_sumcheck_round(cudaStream_t st, void* a, void* b, void* c, void* e
 int launch_whir_sumcheck_round(cudaStream_t st, const void* p_in, const void* w_in, void* p_out, void* w_out,
                                int log_n, bool has_fold, fr_arg fold, void* partials, void* result);
 
+// interned-CSR sparse matrix x vector (provekit/common/src/sparse_matrix.rs:148-184): out[r] = sum_k
+// interned[val[k]] * x[col[k]] over row r.  The transposed product uses the same kernel on the CSC arrays.
+int launch_spmv(cudaStream_t st, const uint64_t* row_start, const uint32_t* col, const uint32_t* val,
+                const void* interned, const void* x, void* out, size_t num_rows, size_t nnz);
+int launch_mul(cudaStream_t st, const void* a, const void* b, void* out, size_t n);
+
 // K10 gathers
 int launch_gather_rows(cudaStream_t st, const void* leaves, size_t w, const uint64_t* idx_dev, size_t n_idx,
                        void* out);

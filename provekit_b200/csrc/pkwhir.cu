@@ -97,6 +97,13 @@ int pk_ctx_create(int device, pk_ctx** out) {
         pk_ctx_destroy(ctx);
         return PK_ERR_CUDA;
     }
+    {   // keep freed blocks cached in the stream-ordered pool: allocation becomes a pointer bump
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t thr = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     *out = ctx;
     return PK_OK;
 }
@@ -131,7 +138,7 @@ int pk_buf_alloc(pk_ctx* ctx, size_t n, pk_buf** out) {
     *out = nullptr;
     pk_buf* b = new pk_buf();
     b->n = n;
-    cudaError_t e = cudaMalloc(&b->d, n ? n * 32 : 32);
+    cudaError_t e = cudaMallocAsync(&b->d, n ? n * 32 : 32, ctx->stream);
     if (e != cudaSuccess) {
         delete b;
         return set_err(ctx, PK_ERR_OOM, "cudaMalloc(%zu elems): %s", n, cudaGetErrorString(e));
@@ -141,8 +148,10 @@ int pk_buf_alloc(pk_ctx* ctx, size_t n, pk_buf** out) {
 }
 void pk_buf_free(pk_ctx* ctx, pk_buf* b) {
     if (!b) return;
-    if (ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(b->d);
+    if (ctx && ctx->stream)
+        cudaFreeAsync(b->d, ctx->stream);  // stream-ordered: no host synchronisation
+    else
+        cudaFree(b->d);
     delete b;
 }
 size_t pk_buf_len(const pk_buf* b) { return b ? b->n : 0; }
@@ -299,7 +308,8 @@ int pk_commit_batch(pk_ctx* ctx, const pk_buf* const* coeffs, int batch, int log
     c->w = ((size_t)batch) << fold;
     c->L = (size_t)1 << (log_n + log_inv_rate - fold);
     c->depth = log_n + log_inv_rate - fold;
-    if (cudaMalloc(&c->leaves, c->L * c->w * 32) != cudaSuccess || cudaMalloc(&c->nodes, 2 * c->L * 32) != cudaSuccess) {
+    if (cudaMallocAsync(&c->leaves, c->L * c->w * 32, ctx->stream) != cudaSuccess ||
+        cudaMallocAsync(&c->nodes, 2 * c->L * 32, ctx->stream) != cudaSuccess) {
         pk_commit_free(ctx, c);
         return set_err(ctx, PK_ERR_OOM, "commit_batch: out of device memory");
     }
@@ -325,9 +335,13 @@ int pk_commit_batch(pk_ctx* ctx, const pk_buf* const* coeffs, int batch, int log
 }
 void pk_commit_free(pk_ctx* ctx, pk_commitment* c) {
     if (!c) return;
-    if (ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(c->leaves);
-    cudaFree(c->nodes);
+    if (ctx && ctx->stream) {
+        if (c->leaves) cudaFreeAsync(c->leaves, ctx->stream);
+        if (c->nodes) cudaFreeAsync(c->nodes, ctx->stream);
+    } else {
+        cudaFree(c->leaves);
+        cudaFree(c->nodes);
+    }
     delete c;
 }
 size_t pk_commit_num_leaves(const pk_commitment* c) { return c ? c->L : 0; }
