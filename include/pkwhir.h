@@ -168,11 +168,22 @@ int pk_prover_create(pk_ctx *ctx, const pk_r1cs *r1cs, pk_prover **out);
 void pk_prover_destroy(pk_prover *p);
 /* returns the spongefish NARG string (= WhirR1CSProof.transcript); *out is malloc'd, free with pk_free */
 int pk_prove(pk_prover *p, const uint64_t *witness, const pk_rand *rnd, uint8_t **out, size_t *out_len);
+/* the two halves of pk_prove, exposed so that a caller can keep one proof's inputs resident in HBM:
+ * H2D staging of witness + masks, then the proof itself from the staged inputs (repeatable). */
+int pk_prover_upload_inputs(pk_prover *p, const uint64_t *witness, const pk_rand *rnd);
+int pk_prove_staged(pk_prover *p, uint8_t **out, size_t *out_len);
 void pk_free(void *p);
-/* host wall-clock seconds per stage of the last pk_prove: [0] witness commit (NTT+Merkle), [1] unused,
+/* host wall-clock seconds per stage of the last pk_prove: [0] witness commit (NTT+Merkle), [1] H2D staging of the inputs,
  * [2] zk-sumcheck, [3] WHIR sumcheck rounds, [4] PoW, [5] STIR openings, [6] R1CS mat-vec + weights,
  * [7] everything else, [8] total */
 void pk_prover_timings(const pk_prover *p, double out[9]);
+
+/* ---- measurement: CUDA-event timing per kernel class on the ctx stream (no reference counterpart).
+ * Between begin and end every launch group is bracketed by an event pair.  Classes: 0 RS-encode NTT
+ * passes, 1 Merkle leaf hashing, 2 Merkle upper levels, 3 zk-sumcheck rounds, 4 WHIR sumcheck rounds,
+ * 5 wavelet, 6 PoW scan, 7 unused.  launches_by_class counts bracketed launch groups. */
+int pk_profile_begin(pk_ctx *ctx);
+int pk_profile_end(pk_ctx *ctx, double ms_by_class[8], uint64_t launches_by_class[8]);
 
 /* ---- measurement helper (no reference counterpart): `iters` dependent Montgomery multiplications
  * in two chains per thread on n_threads threads; *ms_out = device time.  Gives the modmul/s ceiling

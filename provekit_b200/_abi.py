@@ -91,6 +91,10 @@ def lib() -> ctypes.CDLL:
         "pk_prove": (c_int, [vp, u64p, POINTER(Rand), POINTER(vp), POINTER(sz)]),
         "pk_free": (None, [vp]),
         "pk_prover_timings": (None, [vp, POINTER(c_double)]),
+        "pk_profile_begin": (c_int, [vp]),
+        "pk_profile_end": (c_int, [vp, POINTER(c_double), POINTER(c_uint64)]),
+        "pk_prover_upload_inputs": (c_int, [vp, u64p, POINTER(Rand)]),
+        "pk_prove_staged": (c_int, [vp, POINTER(vp), POINTER(sz)]),
         "pk_modmul_bench": (c_int, [vp, sz, c_int, POINTER(c_float)]),
     }
     missing = [n for n in sig if not hasattr(L, n)]

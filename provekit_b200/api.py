@@ -238,15 +238,32 @@ class Prover:
         ctx._chk(ctx.L.pk_prover_create(ctx.h, byref(s), byref(h)))
         self.h = h
 
-    def prove(self, witness, rand: dict) -> bytes:
-        w = _fe(witness)
+    def _rand(self, rand: dict):
         arrs = [_fe(rand[k]) for k in ("mask_w", "g_w", "blind", "mask_h", "g_h")]
-        rs = _abi.Rand(*[a.ctypes.data for a in arrs])
-        out, n = c_void_p(), c_size_t()
-        self.ctx._chk(self.ctx.L.pk_prove(self.h, _p(w), byref(rs), byref(out), byref(n)))
+        return _abi.Rand(*[a.ctypes.data for a in arrs]), arrs
+
+    def _take(self, out, n) -> bytes:
         data = ctypes.string_at(out, n.value)
         self.ctx.L.pk_free(out)
         return data
+
+    def prove(self, witness, rand: dict) -> bytes:
+        """Host buffers in, spongefish NARG string (WhirR1CSProof.transcript) out."""
+        w = _fe(witness)
+        rs, _keep = self._rand(rand)
+        out, n = c_void_p(), c_size_t()
+        self.ctx._chk(self.ctx.L.pk_prove(self.h, _p(w), byref(rs), byref(out), byref(n)))
+        return self._take(out, n)
+
+    def upload_inputs(self, witness, rand: dict):
+        w = _fe(witness)
+        rs, _keep = self._rand(rand)
+        self.ctx._chk(self.ctx.L.pk_prover_upload_inputs(self.h, _p(w), byref(rs)))
+
+    def prove_staged(self) -> bytes:
+        out, n = c_void_p(), c_size_t()
+        self.ctx._chk(self.ctx.L.pk_prove_staged(self.h, byref(out), byref(n)))
+        return self._take(out, n)
 
     def timings(self):
         t = (c_double * 9)()

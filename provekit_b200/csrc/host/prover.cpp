@@ -170,6 +170,10 @@ struct pk_prover {
     void* d_interned = nullptr;
     DevCsr A, B, At, Bt, Ct;  // rows of A,B for M*z; transposes (CSC) of A,B,C for eq^T*M
     double timings[9] = {0};
+    // staged inputs (pk_prover_upload_inputs): [z || mask_w], g_w, [blind || mask_h], g_h in evaluation form
+    pk_buf *masked_w = nullptr, *g_w = nullptr, *masked_h = nullptr, *g_h = nullptr;
+    std::vector<Fr> blind;
+    bool staged = false;
 };
 
 namespace {
@@ -205,7 +209,7 @@ struct Commitment {
 class Prover {
    public:
     Prover(pk_prover* p, pkh::ProverState& fs) : P(p), ctx(p->ctx), fs(fs) {}
-    int run(const uint64_t* witness, const pk_rand* rnd);
+    int run();
 
    private:
     pk_prover* P;
@@ -463,20 +467,13 @@ int Prover::whir_prove(const WhirCfg& cfg, Commitment* cm, pk_buf* const* weight
     return PK_OK;
 }
 
-int Prover::run(const uint64_t* witness, const pk_rand* rnd) {
-    std::memset(P->timings, 0, sizeof P->timings);
+int Prover::run() {
     const double t_start = now_s();
     const int m = P->m, m0 = P->m0, mh = P->mh;
-    const size_t half = (size_t)1 << (m - 1), N = (size_t)1 << m, N0 = (size_t)1 << m0;
+    const size_t N = (size_t)1 << m, N0 = (size_t)1 << m0;
     const size_t nw = P->num_witnesses, nc = P->num_constraints;
-
-    // [f || mask] and g in evaluation form (create_masked_polynomial, zk_utils.rs:3-11)
-    Buf masked_w(ctx, N), g_w(ctx, N);
-    if (!masked_w.b || !g_w.b) return pk::set_err(ctx, PK_ERR_OOM, "prove: out of device memory");
-    PK_TRY(pk_buf_zero(ctx, masked_w, 0, half));
-    PK_TRY(pk_buf_upload(ctx, masked_w, 0, witness, nw));
-    PK_TRY(pk_buf_upload(ctx, masked_w, half, rnd->mask_w, half));
-    PK_TRY(pk_buf_upload(ctx, g_w, 0, rnd->g_w, N));
+    // [f || mask] and g in evaluation form were staged by pk_prover_upload_inputs
+    pk_buf *masked_w = P->masked_w, *g_w = P->g_w, *masked_h = P->masked_h, *g_h = P->g_h;
     Commitment cmw(ctx);
     PK_TRY(batch_commit(m, masked_w, g_w, &cmw, true));
 
@@ -491,20 +488,14 @@ int Prover::run(const uint64_t* witness, const pk_rand* rnd) {
     PK_TRY(pk_buf_zero(ctx, c, 0, N0));
     PK_TRY(pk_buf_zero(ctx, eq, 0, N0));
     // calculate_witness_bounds (sumcheck.rs:181-193): a = A z, b = B z, c = a o b; z = first nw of masked_w
-    ctx->launches += pk::launch_spmv(ctx->stream, P->A.row_start, P->A.col, P->A.val, P->d_interned, masked_w.b->d, a.b->d, nc, P->A.nnz);
-    ctx->launches += pk::launch_spmv(ctx->stream, P->B.row_start, P->B.col, P->B.val, P->d_interned, masked_w.b->d, b.b->d, nc, P->B.nnz);
+    ctx->launches += pk::launch_spmv(ctx->stream, P->A.row_start, P->A.col, P->A.val, P->d_interned, masked_w->d, a.b->d, nc, P->A.nnz);
+    ctx->launches += pk::launch_spmv(ctx->stream, P->B.row_start, P->B.col, P->B.val, P->d_interned, masked_w->d, b.b->d, nc, P->B.nnz);
     ctx->launches += pk::launch_mul(ctx->stream, a.b->d, b.b->d, c.b->d, nc);
     PK_TRY(pk_eval_eq(ctx, r[0].l, m0, pkh::ONE.l, eq));
     T()[6] += now_s() - t0;
 
-    const Fr* blind = reinterpret_cast<const Fr*>(rnd->blind);
-    const size_t halfh = (size_t)1 << (mh - 1), Nh = (size_t)1 << mh;
-    Buf masked_h(ctx, Nh), g_h(ctx, Nh);
-    if (!masked_h.b || !g_h.b) return pk::set_err(ctx, PK_ERR_OOM, "prove: out of device memory");
-    PK_TRY(pk_buf_zero(ctx, masked_h, 0, halfh));
-    PK_TRY(pk_buf_upload(ctx, masked_h, 0, rnd->blind, 4 * (size_t)m0));
-    PK_TRY(pk_buf_upload(ctx, masked_h, halfh, rnd->mask_h, halfh));
-    PK_TRY(pk_buf_upload(ctx, g_h, 0, rnd->g_h, Nh));
+    const Fr* blind = P->blind.data();
+    const size_t Nh = (size_t)1 << mh;
     Commitment cmh(ctx);
     PK_TRY(batch_commit(mh, masked_h, g_h, &cmh, false));
 
@@ -588,8 +579,8 @@ int Prover::run(const uint64_t* witness, const pk_rand* rnd) {
     pk_buf* ws[3] = {*wts[0], *wts[1], *wts[2]};
     PK_TRY(whir_prove(P->cw, &cmw, ws, stmts, 3));
     PK_TRY(pk_ctx_sync(ctx));
-    T()[8] = now_s() - t_start;
-    T()[7] = T()[8] - (T()[0] + T()[2] + T()[3] + T()[4] + T()[5] + T()[6]);
+    T()[8] += now_s() - t_start;
+    T()[7] = T()[8] - (T()[0] + T()[1] + T()[2] + T()[3] + T()[4] + T()[5] + T()[6]);
     return PK_OK;
 }
 
@@ -680,6 +671,10 @@ void pk_prover_destroy(pk_prover* p) {
     if (!p) return;
     cudaStreamSynchronize(p->ctx->stream);
     cudaFree(p->d_interned);
+    pk_buf_free(p->ctx, p->masked_w);
+    pk_buf_free(p->ctx, p->g_w);
+    pk_buf_free(p->ctx, p->masked_h);
+    pk_buf_free(p->ctx, p->g_h);
     free_csr(p->A);
     free_csr(p->B);
     free_csr(p->At);
@@ -687,14 +682,51 @@ void pk_prover_destroy(pk_prover* p) {
     free_csr(p->Ct);
     delete p;
 }
-int pk_prove(pk_prover* p, const uint64_t* witness, const pk_rand* rnd, uint8_t** out, size_t* out_len) {
+// H2D staging of one proof's inputs: witness (zero-padded) || mask, g, blinding cubics || mask, g
+int pk_prover_upload_inputs(pk_prover* p, const uint64_t* witness, const pk_rand* rnd) {
     if (!p) return PK_ERR_INVALID_ARG;
     pk_ctx* ctx = p->ctx;
-    PK_CHECK(ctx, witness && rnd && out && out_len, "prove: null argument");
-    PK_CHECK(ctx, rnd->mask_w && rnd->g_w && rnd->blind && rnd->mask_h && rnd->g_h, "prove: null randomness");
+    PK_CHECK(ctx, witness && rnd, "upload_inputs: null argument");
+    PK_CHECK(ctx, rnd->mask_w && rnd->g_w && rnd->blind && rnd->mask_h && rnd->g_h, "upload_inputs: null randomness");
+    const size_t half = (size_t)1 << (p->m - 1), N = (size_t)1 << p->m;
+    const size_t halfh = (size_t)1 << (p->mh - 1), Nh = (size_t)1 << p->mh;
+    if (!p->masked_w) {
+        PK_TRY(pk_buf_alloc(ctx, N, &p->masked_w));
+        PK_TRY(pk_buf_alloc(ctx, N, &p->g_w));
+        PK_TRY(pk_buf_alloc(ctx, Nh, &p->masked_h));
+        PK_TRY(pk_buf_alloc(ctx, Nh, &p->g_h));
+    }
+    double t0 = now_s();
+    cudaStream_t st = ctx->stream;
+    // create_masked_polynomial (zk_utils.rs:3-11): [pad_to_power_of_two(witness) || mask]
+    PK_CUDA(ctx, cudaMemsetAsync((char*)p->masked_w->d + p->num_witnesses * 32, 0, (half - p->num_witnesses) * 32, st));
+    PK_CUDA(ctx, cudaMemcpyAsync(p->masked_w->d, witness, p->num_witnesses * 32, cudaMemcpyHostToDevice, st));
+    PK_CUDA(ctx, cudaMemcpyAsync((char*)p->masked_w->d + half * 32, rnd->mask_w, half * 32, cudaMemcpyHostToDevice, st));
+    PK_CUDA(ctx, cudaMemcpyAsync(p->g_w->d, rnd->g_w, N * 32, cudaMemcpyHostToDevice, st));
+    PK_CUDA(ctx, cudaMemsetAsync(p->masked_h->d, 0, halfh * 32, st));
+    PK_CUDA(ctx, cudaMemcpyAsync(p->masked_h->d, rnd->blind, 4 * (size_t)p->m0 * 32, cudaMemcpyHostToDevice, st));
+    PK_CUDA(ctx, cudaMemcpyAsync((char*)p->masked_h->d + halfh * 32, rnd->mask_h, halfh * 32, cudaMemcpyHostToDevice, st));
+    PK_CUDA(ctx, cudaMemcpyAsync(p->g_h->d, rnd->g_h, Nh * 32, cudaMemcpyHostToDevice, st));
+    p->blind.assign(reinterpret_cast<const Fr*>(rnd->blind), reinterpret_cast<const Fr*>(rnd->blind) + 4 * (size_t)p->m0);
+    PK_CUDA(ctx, cudaStreamSynchronize(st));
+    std::memset(p->timings, 0, sizeof p->timings);
+    p->timings[1] = now_s() - t0;  // H2D staging time
+    p->timings[8] = p->timings[1];
+    p->staged = true;
+    return PK_OK;
+}
+int pk_prove_staged(pk_prover* p, uint8_t** out, size_t* out_len) {
+    if (!p) return PK_ERR_INVALID_ARG;
+    pk_ctx* ctx = p->ctx;
+    PK_CHECK(ctx, out && out_len, "prove: null argument");
+    PK_CHECK(ctx, p->staged, "prove_staged: call pk_prover_upload_inputs first");
+    double keep1 = p->timings[1];
+    std::memset(p->timings, 0, sizeof p->timings);
+    p->timings[1] = keep1;
+    p->timings[8] = keep1;
     pkh::ProverState fs(p->domsep);
     Prover pr(p, fs);
-    PK_TRY(pr.run(witness, rnd));
+    PK_TRY(pr.run());
     std::vector<uint8_t>& narg = fs.narg();
     uint8_t* buf = (uint8_t*)std::malloc(narg.size() ? narg.size() : 1);
     if (!buf) return pk::set_err(ctx, PK_ERR_OOM, "prove: host allocation failed");
@@ -702,6 +734,11 @@ int pk_prove(pk_prover* p, const uint64_t* witness, const pk_rand* rnd, uint8_t*
     *out = buf;
     *out_len = narg.size();
     return PK_OK;
+}
+int pk_prove(pk_prover* p, const uint64_t* witness, const pk_rand* rnd, uint8_t** out, size_t* out_len) {
+    PK_TRY(pk_prover_upload_inputs(p, witness, rnd));
+    int rc = pk_prove_staged(p, out, out_len);
+    return rc;
 }
 void pk_free(void* p) { std::free(p); }
 void pk_prover_timings(const pk_prover* p, double out[9]) {

@@ -336,10 +336,12 @@ __global__ void __launch_bounds__(256) k_merkle_top(fr* nodes, int top) {
         __syncthreads();
     }
 }
-int launch_merkle(cudaStream_t st, const void* leaves, size_t L, size_t w, void* nodes) {
-    int launches = 0;
+int launch_merkle_leaves(cudaStream_t st, const void* leaves, size_t L, size_t w, void* nodes) {
     k_merkle_leaves<<<(unsigned)((L + 127) / 128), 128, 0, st>>>((const fr*)leaves, L, (int)w, (fr*)nodes);
-    launches++;
+    return 1;
+}
+int launch_merkle_upper(cudaStream_t st, size_t L, void* nodes) {
+    int launches = 0;
     size_t lvl = L / 2;
     for (; lvl > 256; lvl >>= 1) {
         k_merkle_level<<<(unsigned)((lvl + 127) / 128), 128, 0, st>>>((fr*)nodes, lvl);

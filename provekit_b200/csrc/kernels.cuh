@@ -30,7 +30,8 @@ int launch_rs_encode(cudaStream_t st, const void* coeffs, int log_n, int log_inv
                      size_t leaf_stride, size_t col_offset, void* scratch, const void* table, int table_log_m);
 
 // K2 Merkle: leaves Montgomery, nodes canonical heap order
-int launch_merkle(cudaStream_t st, const void* leaves, size_t L, size_t w, void* nodes);
+int launch_merkle_leaves(cudaStream_t st, const void* leaves, size_t L, size_t w, void* nodes);
+int launch_merkle_upper(cudaStream_t st, size_t L, void* nodes);
 
 // tensor-product tables: for point k (k < K) and variable j (j < nv, point[k*pt_stride + var_off + j]):
 //   T_k[idx] = scale_k * prod_j (bit_{nv-1-j}(idx) ? f1 : f0),   eq: (f0,f1) = (1-x, x);  pow: (1, x)

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <vector>
 
 #include "../../include/pkwhir.h"
 #include "kernels.cuh"
@@ -31,6 +32,12 @@ struct pk_ctx {
     size_t small_bytes = 0;
     void* h_stage = nullptr;      // pinned staging for uploads/downloads
     size_t h_stage_bytes = 0;
+    // optional per-kernel-class CUDA-event timing (pk_profile_begin/end)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    struct EvSpan { int cls; size_t a, b; };
+    std::vector<EvSpan> ev_spans;
+    size_t ev_used = 0;
 };
 
 struct pk_buf {
@@ -46,6 +53,34 @@ struct pk_commitment {
 };
 
 namespace pk {
+enum ProfClass { PROF_NTT = 0, PROF_MERKLE_LEAVES, PROF_MERKLE_UPPER, PROF_ZK_SUMCHECK, PROF_WHIR_SUMCHECK, PROF_WAVELET,
+                 PROF_POW, PROF_OTHER, PROF_NCLASS };
+// records a CUDA-event pair around the launches issued during its lifetime (only while profiling)
+struct ProfScope {
+    pk_ctx* ctx;
+    size_t a = 0;
+    int cls;
+    bool on;
+    ProfScope(pk_ctx* c, int cls_) : ctx(c), cls(cls_), on(c->profiling) {
+        if (!on) return;
+        a = next();
+        cudaEventRecord(ctx->ev_pool[a], ctx->stream);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        size_t b = next();
+        cudaEventRecord(ctx->ev_pool[b], ctx->stream);
+        ctx->ev_spans.push_back({cls, a, b});
+    }
+    size_t next() {
+        if (ctx->ev_used == ctx->ev_pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ctx->ev_pool.push_back(e);
+        }
+        return ctx->ev_used++;
+    }
+};
 int set_err(pk_ctx* ctx, int code, const char* fmt, ...);
 int ensure_twiddles(pk_ctx* ctx, int log_m);
 int ensure_scratch(pk_ctx* ctx, size_t elems);

@@ -119,6 +119,7 @@ void pk_ctx_destroy(pk_ctx* ctx) {
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_tables);
     cudaFree(ctx->d_small);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -248,7 +249,10 @@ int pk_pow_solve(pk_ctx* ctx, const uint64_t challenge[4], double bits, uint64_t
     double want = std::exp2(bits + 1.0);
     while ((double)chunk < want && chunk < ((uint64_t)1 << 28)) chunk <<= 1;
     for (uint64_t base = 0;; base += chunk) {
-        ctx->launches += launch_pow_scan(ctx->stream, to_arg(challenge), to_arg(thr), base, chunk, ctx->d_best);
+        {
+            ProfScope ps(ctx, PROF_POW);
+            ctx->launches += launch_pow_scan(ctx->stream, to_arg(challenge), to_arg(thr), base, chunk, ctx->d_best);
+        }
         PK_CUDA(ctx, cudaGetLastError());
         PK_CUDA(ctx, cudaMemcpyAsync(ctx->h_result, ctx->d_best, 8, cudaMemcpyDeviceToHost, ctx->stream));
         PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -263,7 +267,10 @@ int pk_pow_solve(pk_ctx* ctx, const uint64_t challenge[4], double bits, uint64_t
 // ---- wavelet -----------------------------------------------------------------------------------
 static int wavelet(pk_ctx* ctx, pk_buf* buf, int log_n, bool inverse) {
     PK_CHECK(ctx, buf && log_n >= 0 && log_n < 40 && ((size_t)1 << log_n) <= buf->n, "wavelet: 2^%d exceeds buffer", log_n);
-    ctx->launches += launch_wavelet(ctx->stream, buf->d, log_n, inverse);
+    {
+        ProfScope ps(ctx, PROF_WAVELET);
+        ctx->launches += launch_wavelet(ctx->stream, buf->d, log_n, inverse);
+    }
     PK_CUDA(ctx, cudaGetLastError());
     return PK_OK;
 }
@@ -278,8 +285,11 @@ static int rs_encode_raw(pk_ctx* ctx, const void* coeffs, int log_n, int log_inv
     int logM = log_n - fold + log_inv_rate;
     PK_TRY(ensure_twiddles(ctx, logM));
     PK_TRY(ensure_scratch(ctx, (size_t)1 << (log_n + log_inv_rate)));
-    ctx->launches += launch_rs_encode(ctx->stream, coeffs, log_n, log_inv_rate, fold, leaves, leaf_stride, col_offset,
-                                      ctx->d_scratch, ctx->d_twiddles, ctx->twiddle_log_m);
+    {
+        ProfScope ps(ctx, PROF_NTT);
+        ctx->launches += launch_rs_encode(ctx->stream, coeffs, log_n, log_inv_rate, fold, leaves, leaf_stride, col_offset,
+                                          ctx->d_scratch, ctx->d_twiddles, ctx->twiddle_log_m);
+    }
     PK_CUDA(ctx, cudaGetLastError());
     return PK_OK;
 }
@@ -295,7 +305,14 @@ int pk_merkle_build(pk_ctx* ctx, const pk_buf* leaves, size_t L, size_t w, pk_bu
     if (w == 0) return set_err(ctx, PK_ERR_EMPTY_INPUT, "IncorrectInputLength(0)");
     PK_CHECK(ctx, L >= 2 && (L & (L - 1)) == 0, "merkle_build: leaf count must be a power of two >= 2");
     PK_CHECK(ctx, leaves->n >= L * w && nodes->n >= 2 * L, "merkle_build: buffer too small");
-    ctx->launches += launch_merkle(ctx->stream, leaves->d, L, w, nodes->d);
+    {
+        ProfScope ps(ctx, PROF_MERKLE_LEAVES);
+        ctx->launches += launch_merkle_leaves(ctx->stream, leaves->d, L, w, nodes->d);
+    }
+    {
+        ProfScope ps(ctx, PROF_MERKLE_UPPER);
+        ctx->launches += launch_merkle_upper(ctx->stream, L, nodes->d);
+    }
     PK_CUDA(ctx, cudaGetLastError());
     return PK_OK;
 }
@@ -320,7 +337,14 @@ int pk_commit_batch(pk_ctx* ctx, const pk_buf* const* coeffs, int batch, int log
             return rc;
         }
     }
-    ctx->launches += launch_merkle(ctx->stream, c->leaves, c->L, c->w, c->nodes);
+    {
+        ProfScope ps(ctx, PROF_MERKLE_LEAVES);
+        ctx->launches += launch_merkle_leaves(ctx->stream, c->leaves, c->L, c->w, c->nodes);
+    }
+    {
+        ProfScope ps(ctx, PROF_MERKLE_UPPER);
+        ctx->launches += launch_merkle_upper(ctx->stream, c->L, c->nodes);
+    }
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_result, (char*)c->nodes + 32, 32, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -488,8 +512,11 @@ int pk_zk_sumcheck_round(pk_ctx* ctx, pk_buf* a, pk_buf* b, pk_buf* c, pk_buf* e
     PK_CHECK(ctx, a->n >= n && b->n >= n && c->n >= n && eq->n >= n, "zk_sumcheck_round: arrays shorter than 2^log_n");
     fr_arg f = {};
     if (fold) f = to_arg(fold);
-    ctx->launches += launch_zk_sumcheck_round(ctx->stream, a->d, b->d, c->d, eq->d, log_n, fold != nullptr, f, ctx->d_partials,
-                                              ctx->d_result);
+    {
+        ProfScope ps(ctx, PROF_ZK_SUMCHECK);
+        ctx->launches += launch_zk_sumcheck_round(ctx->stream, a->d, b->d, c->d, eq->d, log_n, fold != nullptr, f, ctx->d_partials,
+                                                  ctx->d_result);
+    }
     return fetch_result(ctx, out3, 3);
 }
 int pk_whir_sumcheck_round(pk_ctx* ctx, const pk_buf* p_in, const pk_buf* w_in, pk_buf* p_out, pk_buf* w_out, int log_n,
@@ -504,9 +531,40 @@ int pk_whir_sumcheck_round(pk_ctx* ctx, const pk_buf* p_in, const pk_buf* w_in, 
         PK_CHECK(ctx, p_out->d != p_in->d && w_out->d != w_in->d, "whir_sumcheck_round: folding needs distinct output buffers");
         f = to_arg(fold);
     }
-    ctx->launches += launch_whir_sumcheck_round(ctx->stream, p_in->d, w_in->d, fold ? p_out->d : nullptr, fold ? w_out->d : nullptr,
-                                                log_n, fold != nullptr, f, ctx->d_partials, ctx->d_result);
+    {
+        ProfScope ps(ctx, PROF_WHIR_SUMCHECK);
+        ctx->launches += launch_whir_sumcheck_round(ctx->stream, p_in->d, w_in->d, fold ? p_out->d : nullptr,
+                                                    fold ? w_out->d : nullptr, log_n, fold != nullptr, f, ctx->d_partials, ctx->d_result);
+    }
     return fetch_result(ctx, out3, 3);
+}
+
+// ---- per-kernel-class device timing (CUDA events on the ctx stream) --------------------------------
+int pk_profile_begin(pk_ctx* ctx) {
+    if (!ctx) return PK_ERR_INVALID_ARG;
+    PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->profiling = true;
+    ctx->ev_spans.clear();
+    ctx->ev_used = 0;
+    return PK_OK;
+}
+int pk_profile_end(pk_ctx* ctx, double ms_by_class[8], uint64_t launches_by_class[8]) {
+    if (!ctx || !ms_by_class || !launches_by_class) return PK_ERR_INVALID_ARG;
+    PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 8; i++) {
+        ms_by_class[i] = 0;
+        launches_by_class[i] = 0;
+    }
+    for (const pk_ctx::EvSpan& s : ctx->ev_spans) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev_pool[s.a], ctx->ev_pool[s.b]);
+        ms_by_class[s.cls] += ms;
+        launches_by_class[s.cls] += 1;
+    }
+    ctx->profiling = false;
+    ctx->ev_spans.clear();
+    ctx->ev_used = 0;
+    return PK_OK;
 }
 
 // ---- measurement helper (not part of the reference surface) ----------------------------------------
