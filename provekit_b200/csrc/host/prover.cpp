@@ -157,7 +157,20 @@ struct DevCsr {
     uint64_t* row_start = nullptr;
     uint32_t *col = nullptr, *val = nullptr;
     size_t rows = 0, nnz = 0;
+    // rows longer than pk::SPMV_LONG_ROW, split into chunks (see kernels.cuh)
+    uint64_t *chunk_start = nullptr, *chunk_end = nullptr;
+    uint32_t *long_row = nullptr, *long_first = nullptr, *long_cnt = nullptr;
+    void* chunk_partials = nullptr;
+    size_t n_chunks = 0, n_long = 0;
 };
+// out = M * x on the device (short rows: thread per row; long rows: chunked)
+int spmv(pk_ctx* ctx, const DevCsr& M, const void* interned, const void* x, void* out, size_t rows) {
+    ctx->launches += pk::launch_spmv(ctx->stream, M.row_start, M.col, M.val, interned, x, out, rows, M.nnz);
+    ctx->launches += pk::launch_spmv_long(ctx->stream, M.col, M.val, interned, x, out, M.chunk_start, M.chunk_end, M.n_chunks,
+                                          M.long_row, M.long_first, M.long_cnt, M.n_long, M.chunk_partials);
+    PK_CUDA(ctx, cudaGetLastError());
+    return PK_OK;
+}
 
 }  // namespace
 
@@ -488,8 +501,8 @@ int Prover::run() {
     PK_TRY(pk_buf_zero(ctx, c, 0, N0));
     PK_TRY(pk_buf_zero(ctx, eq, 0, N0));
     // calculate_witness_bounds (sumcheck.rs:181-193): a = A z, b = B z, c = a o b; z = first nw of masked_w
-    ctx->launches += pk::launch_spmv(ctx->stream, P->A.row_start, P->A.col, P->A.val, P->d_interned, masked_w->d, a.b->d, nc, P->A.nnz);
-    ctx->launches += pk::launch_spmv(ctx->stream, P->B.row_start, P->B.col, P->B.val, P->d_interned, masked_w->d, b.b->d, nc, P->B.nnz);
+    PK_TRY(spmv(ctx, P->A, P->d_interned, masked_w->d, a.b->d, nc));
+    PK_TRY(spmv(ctx, P->B, P->d_interned, masked_w->d, b.b->d, nc));
     ctx->launches += pk::launch_mul(ctx->stream, a.b->d, b.b->d, c.b->d, nc);
     PK_TRY(pk_eval_eq(ctx, r[0].l, m0, pkh::ONE.l, eq));
     T()[6] += now_s() - t0;
@@ -561,8 +574,7 @@ int Prover::run() {
     Fr f_sums[3], g_sums[3], stmts[3];
     for (int j = 0; j < 3; j++) {
         PK_TRY(pk_buf_zero(ctx, *wts[j], 0, N));
-        ctx->launches += pk::launch_spmv(ctx->stream, T3[j]->row_start, T3[j]->col, T3[j]->val, P->d_interned, eq_alpha.b->d,
-                                         wts[j]->b->d, nw, T3[j]->nnz);
+        PK_TRY(spmv(ctx, *T3[j], P->d_interned, eq_alpha.b->d, wts[j]->b->d, nw));
         PK_TRY(pk_dot(ctx, *wts[j], masked_w, N, f_sums[j].l));
         PK_TRY(pk_dot(ctx, *wts[j], g_w, N, g_sums[j].l));
         stmts[j] = pkh::add(f_sums[j], pkh::mul(cmw.batching, g_sums[j]));
@@ -594,6 +606,36 @@ int upload_csr_arrays(pk_ctx* ctx, const std::vector<uint64_t>& rs, const std::v
     PK_CUDA(ctx, cudaMemcpy(out->row_start, rs.data(), rs.size() * 8, cudaMemcpyHostToDevice));
     PK_CUDA(ctx, cudaMemcpy(out->col, col.data(), col.size() * 4, cudaMemcpyHostToDevice));
     PK_CUDA(ctx, cudaMemcpy(out->val, val.data(), val.size() * 4, cudaMemcpyHostToDevice));
+    // long rows -> chunks
+    std::vector<uint64_t> cs, ce;
+    std::vector<uint32_t> lrow, lfirst, lcnt;
+    for (size_t r = 0; r < rs.size(); r++) {
+        uint64_t s = rs[r], e = r + 1 < rs.size() ? rs[r + 1] : col.size();
+        if (e - s <= (uint64_t)pk::SPMV_LONG_ROW) continue;
+        lrow.push_back((uint32_t)r);
+        lfirst.push_back((uint32_t)cs.size());
+        uint32_t n = 0;
+        for (uint64_t k = s; k < e; k += pk::SPMV_CHUNK, n++) {
+            cs.push_back(k);
+            ce.push_back(k + pk::SPMV_CHUNK < e ? k + pk::SPMV_CHUNK : e);
+        }
+        lcnt.push_back(n);
+    }
+    out->n_chunks = cs.size();
+    out->n_long = lrow.size();
+    if (out->n_long) {
+        PK_CUDA(ctx, cudaMalloc((void**)&out->chunk_start, cs.size() * 8));
+        PK_CUDA(ctx, cudaMalloc((void**)&out->chunk_end, cs.size() * 8));
+        PK_CUDA(ctx, cudaMalloc((void**)&out->long_row, lrow.size() * 4));
+        PK_CUDA(ctx, cudaMalloc((void**)&out->long_first, lrow.size() * 4));
+        PK_CUDA(ctx, cudaMalloc((void**)&out->long_cnt, lrow.size() * 4));
+        PK_CUDA(ctx, cudaMalloc(&out->chunk_partials, cs.size() * 32));
+        PK_CUDA(ctx, cudaMemcpy(out->chunk_start, cs.data(), cs.size() * 8, cudaMemcpyHostToDevice));
+        PK_CUDA(ctx, cudaMemcpy(out->chunk_end, ce.data(), ce.size() * 8, cudaMemcpyHostToDevice));
+        PK_CUDA(ctx, cudaMemcpy(out->long_row, lrow.data(), lrow.size() * 4, cudaMemcpyHostToDevice));
+        PK_CUDA(ctx, cudaMemcpy(out->long_first, lfirst.data(), lfirst.size() * 4, cudaMemcpyHostToDevice));
+        PK_CUDA(ctx, cudaMemcpy(out->long_cnt, lcnt.data(), lcnt.size() * 4, cudaMemcpyHostToDevice));
+    }
     return PK_OK;
 }
 int check_csr(pk_ctx* ctx, const pk_csr& m, uint64_t rows, uint64_t cols, uint64_t n_interned) {
@@ -633,6 +675,12 @@ void free_csr(DevCsr& c) {
     cudaFree(c.row_start);
     cudaFree(c.col);
     cudaFree(c.val);
+    cudaFree(c.chunk_start);
+    cudaFree(c.chunk_end);
+    cudaFree(c.long_row);
+    cudaFree(c.long_first);
+    cudaFree(c.long_cnt);
+    cudaFree(c.chunk_partials);
 }
 
 }  // namespace

@@ -579,9 +579,39 @@ __global__ void __launch_bounds__(256) k_spmv(const uint64_t* __restrict__ row_s
     size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= num_rows) return;
     size_t s = row_start[r], e = r + 1 < num_rows ? row_start[r + 1] : nnz;
+    if (e - s > (size_t)SPMV_LONG_ROW) return;  // handled by k_spmv_long_*
     fr acc = fr_zero();
     for (size_t k = s; k < e; k++) acc = fr_add(acc, fr_mul(fr_load_nc(&interned[val[k]]), fr_load_nc(&x[col[k]])));
     fr_store(&out[r], acc);
+}
+__global__ void __launch_bounds__(256) k_spmv_long_chunks(const uint32_t* __restrict__ col, const uint32_t* __restrict__ val,
+                                                          const fr* __restrict__ interned, const fr* __restrict__ x,
+                                                          const uint64_t* __restrict__ chunk_start,
+                                                          const uint64_t* __restrict__ chunk_end, fr* partials) {
+    size_t s = chunk_start[blockIdx.x], e = chunk_end[blockIdx.x];
+    fr acc[1] = {fr_zero()};
+    for (size_t k = s + threadIdx.x; k < e; k += blockDim.x)
+        acc[0] = fr_add(acc[0], fr_mul(fr_load_nc(&interned[val[k]]), fr_load_nc(&x[col[k]])));
+    block_reduce<1>(acc, &partials[blockIdx.x]);
+}
+__global__ void __launch_bounds__(32) k_spmv_long_rows(const fr* __restrict__ partials, const uint32_t* __restrict__ long_row,
+                                                       const uint32_t* __restrict__ long_first,
+                                                       const uint32_t* __restrict__ long_cnt, fr* out) {
+    // one warp per long row
+    uint32_t first = long_first[blockIdx.x], cnt = long_cnt[blockIdx.x];
+    fr acc[1] = {fr_zero()};
+    for (uint32_t c = threadIdx.x; c < cnt; c += 32) acc[0] = fr_add(acc[0], fr_load(&partials[first + c]));
+    block_reduce<1>(acc, &out[long_row[blockIdx.x]]);
+}
+int launch_spmv_long(cudaStream_t st, const uint32_t* col, const uint32_t* val, const void* interned, const void* x,
+                     void* out, const uint64_t* chunk_start, const uint64_t* chunk_end, size_t n_chunks,
+                     const uint32_t* long_row, const uint32_t* long_first, const uint32_t* long_cnt, size_t n_long,
+                     void* chunk_partials) {
+    if (n_long == 0) return 0;
+    k_spmv_long_chunks<<<(unsigned)n_chunks, 256, 0, st>>>(col, val, (const fr*)interned, (const fr*)x, chunk_start, chunk_end,
+                                                         (fr*)chunk_partials);
+    k_spmv_long_rows<<<(unsigned)n_long, 32, 0, st>>>((const fr*)chunk_partials, long_row, long_first, long_cnt, (fr*)out);
+    return 2;
 }
 int launch_spmv(cudaStream_t st, const uint64_t* row_start, const uint32_t* col, const uint32_t* val,
                 const void* interned, const void* x, void* out, size_t num_rows, size_t nnz) {

@@ -57,8 +57,17 @@ int launch_whir_sumcheck_round(cudaStream_t st, const void* p_in, const void* w_
 
 // interned-CSR sparse matrix x vector (provekit/common/src/sparse_matrix.rs:148-184): out[r] = sum_k
 // interned[val[k]] * x[col[k]] over row r.  The transposed product uses the same kernel on the CSC arrays.
+// Rows longer than SPMV_LONG_ROW are skipped by launch_spmv and handled by launch_spmv_long, which splits them
+// into chunks of <= SPMV_CHUNK entries (one block per chunk, then one thread per long row sums its chunks):
+// a constant-one witness column makes one row of the transposed matrix hold millions of entries.
+constexpr int SPMV_LONG_ROW = 64;
+constexpr int SPMV_CHUNK = 2048;
 int launch_spmv(cudaStream_t st, const uint64_t* row_start, const uint32_t* col, const uint32_t* val,
                 const void* interned, const void* x, void* out, size_t num_rows, size_t nnz);
+int launch_spmv_long(cudaStream_t st, const uint32_t* col, const uint32_t* val, const void* interned, const void* x,
+                     void* out, const uint64_t* chunk_start, const uint64_t* chunk_end, size_t n_chunks,
+                     const uint32_t* long_row, const uint32_t* long_first, const uint32_t* long_cnt, size_t n_long,
+                     void* chunk_partials);
 int launch_mul(cudaStream_t st, const void* a, const void* b, void* out, size_t n);
 
 // K10 gathers

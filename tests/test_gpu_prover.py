@@ -67,3 +67,32 @@ def test_bad_witness_is_caught_by_verifier(ctx, orc):
     proof = pr.prove(w, r.randomness())
     assert oracle_verify(orc, r, proof) != 0
     pr.close()
+
+
+def test_hot_column_long_rows(ctx, orc):
+    """A witness column referenced by thousands of entries (constant-one / zero witness) makes one row of
+    the transposed matrices very long: exercises the chunked long-row SpMV path.  Workload generator of
+    bench.py at a small size, checked against the oracle prover and verifier."""
+    import ctypes
+    import provekit_b200 as pk
+    from r1cs_util import CSRc, R1CSc, Randc
+    from tools import workload as wl
+    r = wl.synth_r1cs(5000, 6500, (5200, 4100, 21000), n_interned=40, seed=3)
+    rnd = wl.randomness(r)
+
+    def csr(t):
+        return CSRc(r["num_constraints"], r["num_witnesses"], len(t[1]), t[0].ctypes.data, t[1].ctypes.data, t[2].ctypes.data)
+
+    cs = R1CSc(r["num_constraints"], r["num_witnesses"], len(r["interned"]), r["interned"].ctypes.data,
+               csr(r["a"]), csr(r["b"]), csr(r["c"]))
+    rs = Randc(*[rnd[k].ctypes.data for k in ("mask_w", "g_w", "blind", "mask_h", "g_h")])
+    out = ctypes.c_void_p()
+    n = orc.orc_prove(ctypes.byref(cs), r["witness"].ctypes.data_as(ctypes.c_void_p), ctypes.byref(rs), 2, ctypes.byref(out))
+    expected = ctypes.string_at(out, n)
+    orc.orc_free(out)
+    pr = pk.Prover(ctx, r)
+    got = pr.prove(r["witness"], rnd)
+    assert got == expected
+    buf = np.frombuffer(got, dtype=np.uint8)
+    assert orc.orc_verify(ctypes.byref(cs), buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(got)), 2) == 0
+    pr.close()
