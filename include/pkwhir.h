@@ -181,9 +181,10 @@ void pk_prover_timings(const pk_prover *p, double out[9]);
 /* ---- measurement: CUDA-event timing per kernel class on the ctx stream (no reference counterpart).
  * Between begin and end every launch group is bracketed by an event pair.  Classes: 0 RS-encode NTT
  * passes, 1 Merkle leaf hashing, 2 Merkle upper levels, 3 zk-sumcheck rounds, 4 WHIR sumcheck rounds,
- * 5 wavelet, 6 PoW scan, 7 unused.  launches_by_class counts bracketed launch groups. */
+ * 5 wavelet, 6 PoW scan, 7 unused.  launches_by_class counts bracketed launch groups; max_ms_by_class is
+ * the longest single group of the class (the dominant launch, e.g. the witness-commit leaf hashing). */
 int pk_profile_begin(pk_ctx *ctx);
-int pk_profile_end(pk_ctx *ctx, double ms_by_class[8], uint64_t launches_by_class[8]);
+int pk_profile_end(pk_ctx *ctx, double ms_by_class[8], uint64_t launches_by_class[8], double max_ms_by_class[8]);
 
 /* ---- measurement helper (no reference counterpart): `iters` dependent Montgomery multiplications
  * in two chains per thread on n_threads threads; *ms_out = device time.  Gives the modmul/s ceiling

@@ -92,7 +92,7 @@ def lib() -> ctypes.CDLL:
         "pk_free": (None, [vp]),
         "pk_prover_timings": (None, [vp, POINTER(c_double)]),
         "pk_profile_begin": (c_int, [vp]),
-        "pk_profile_end": (c_int, [vp, POINTER(c_double), POINTER(c_uint64)]),
+        "pk_profile_end": (c_int, [vp, POINTER(c_double), POINTER(c_uint64), POINTER(c_double)]),
         "pk_prover_upload_inputs": (c_int, [vp, u64p, POINTER(Rand)]),
         "pk_prove_staged": (c_int, [vp, POINTER(vp), POINTER(sz)]),
         "pk_modmul_bench": (c_int, [vp, sz, c_int, POINTER(c_float)]),

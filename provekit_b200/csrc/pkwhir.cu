@@ -548,18 +548,20 @@ int pk_profile_begin(pk_ctx* ctx) {
     ctx->ev_used = 0;
     return PK_OK;
 }
-int pk_profile_end(pk_ctx* ctx, double ms_by_class[8], uint64_t launches_by_class[8]) {
-    if (!ctx || !ms_by_class || !launches_by_class) return PK_ERR_INVALID_ARG;
+int pk_profile_end(pk_ctx* ctx, double ms_by_class[8], uint64_t launches_by_class[8], double max_ms_by_class[8]) {
+    if (!ctx || !ms_by_class || !launches_by_class || !max_ms_by_class) return PK_ERR_INVALID_ARG;
     PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 8; i++) {
         ms_by_class[i] = 0;
         launches_by_class[i] = 0;
+        max_ms_by_class[i] = 0;
     }
     for (const pk_ctx::EvSpan& s : ctx->ev_spans) {
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev_pool[s.a], ctx->ev_pool[s.b]);
         ms_by_class[s.cls] += ms;
         launches_by_class[s.cls] += 1;
+        if (ms > max_ms_by_class[s.cls]) max_ms_by_class[s.cls] = ms;
     }
     ctx->profiling = false;
     ctx->ev_spans.clear();
