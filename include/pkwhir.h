@@ -190,6 +190,7 @@ int pk_profile_end(pk_ctx *ctx, double ms_by_class[8], uint64_t launches_by_clas
  * in two chains per thread on n_threads threads; *ms_out = device time.  Gives the modmul/s ceiling
  * of the integer pipe that DESIGN.md quotes next to the HBM roofline. */
 int pk_modmul_bench(pk_ctx *ctx, size_t n_threads, int iters, float *ms_out);
+int pk_modsqr_bench(pk_ctx *ctx, size_t n_threads, int iters, float *ms_out); /* same with the dedicated squaring */
 
 #ifdef __cplusplus
 }

@@ -96,6 +96,7 @@ def lib() -> ctypes.CDLL:
         "pk_prover_upload_inputs": (c_int, [vp, u64p, POINTER(Rand)]),
         "pk_prove_staged": (c_int, [vp, POINTER(vp), POINTER(sz)]),
         "pk_modmul_bench": (c_int, [vp, sz, c_int, POINTER(c_float)]),
+        "pk_modsqr_bench": (c_int, [vp, sz, c_int, POINTER(c_float)]),
     }
     missing = [n for n in sig if not hasattr(L, n)]
     if missing:

@@ -208,9 +208,10 @@ class Context:
                                                 w_out.h if w_out else None, log_n, _p(f), _p(out)))
         return out
 
-    def modmul_bench(self, n_threads: int, iters: int) -> float:
+    def modmul_bench(self, n_threads: int, iters: int, square: bool = False) -> float:
         ms = c_float()
-        self._chk(self.L.pk_modmul_bench(self.h, n_threads, iters, byref(ms)))
+        f = self.L.pk_modsqr_bench if square else self.L.pk_modmul_bench
+        self._chk(f(self.h, n_threads, iters, byref(ms)))
         return ms.value
 
 

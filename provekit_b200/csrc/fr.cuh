@@ -163,14 +163,18 @@ __device__ __forceinline__ fr fr_neg(const fr& a) { return fr_sub(fr_zero(), a);
 // ---- Montgomery multiplier building blocks (each one asm statement = one carry chain) ----------
 // acc[0..7] = x0,x2,x4,x6 (4 limbs) * b : lo -> acc[2k], hi -> acc[2k+1]
 __device__ __forceinline__ void mul4(uint32_t* acc, uint32_t x0, uint32_t x2, uint32_t x4, uint32_t x6, uint32_t b) {
-    asm("mul.lo.u32 %0, %8, %12;\n\t"
-        "mul.hi.u32 %1, %8, %12;\n\t"
-        "mul.lo.u32 %2, %9, %12;\n\t"
-        "mul.hi.u32 %3, %9, %12;\n\t"
-        "mul.lo.u32 %4, %10, %12;\n\t"
-        "mul.hi.u32 %5, %10, %12;\n\t"
-        "mul.lo.u32 %6, %11, %12;\n\t"
-        "mul.hi.u32 %7, %11, %12;"
+    // mul.wide keeps each product ONE IMAD.WIDE (separate mul.lo / mul.hi are not fused by ptxas)
+    asm("{\n\t"
+        ".reg .u64 w;\n\t"
+        "mul.wide.u32 w, %8, %12;\n\t"
+        "mov.b64 {%0, %1}, w;\n\t"
+        "mul.wide.u32 w, %9, %12;\n\t"
+        "mov.b64 {%2, %3}, w;\n\t"
+        "mul.wide.u32 w, %10, %12;\n\t"
+        "mov.b64 {%4, %5}, w;\n\t"
+        "mul.wide.u32 w, %11, %12;\n\t"
+        "mov.b64 {%6, %7}, w;\n\t"
+        "}"
         : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]),
           "=r"(acc[7])
         : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(b));
@@ -252,7 +256,7 @@ __device__ __forceinline__ fr fr_mul(const fr& a, const fr& b) {
           "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]));
     return fr_reduce_once(r);
 }
-__device__ __forceinline__ fr fr_sqr(const fr& a) { return fr_mul(a, a); }
+#include "fr_sqr.inc"
 
 // canonical integer < p  ->  Montgomery form
 __device__ __forceinline__ fr fr_to_mont(const fr& c) { return fr_mul(c, fr_r2()); }

@@ -672,6 +672,9 @@ __global__ void __launch_bounds__(128) k_pow_scan(fr_arg challenge, fr_arg thres
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
     uint64_t nonce = base + t;
+    // a smaller accepted nonce already exists: nothing in this (higher) range can win (fetch_min semantics,
+    // skyscraper/core/src/generic.rs:56-58)
+    if (*reinterpret_cast<volatile unsigned long long*>(best) < nonce) return;
     fr l = sky_reduce(arg_fr(challenge));
     fr r = fr_zero();
     r.v[0] = (uint32_t)nonce;
@@ -707,8 +710,21 @@ __global__ void __launch_bounds__(256) k_modmul_bench(fr* data, int iters) {
     fr_store(&data[2 * i], x);
     fr_store(&data[2 * i + 1], y);
 }
-int launch_modmul_bench(cudaStream_t st, void* data, size_t n_threads, int iters) {
-    k_modmul_bench<<<(unsigned)(n_threads / 256), 256, 0, st>>>((fr*)data, iters);
+__global__ void __launch_bounds__(256) k_modsqr_bench(fr* data, int iters) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    fr x = fr_load(&data[2 * i]), y = fr_load(&data[2 * i + 1]);
+    for (int it = 0; it < iters; it++) {
+        x = fr_sqr(x);
+        y = fr_sqr(y);
+    }
+    fr_store(&data[2 * i], x);
+    fr_store(&data[2 * i + 1], y);
+}
+int launch_modmul_bench(cudaStream_t st, void* data, size_t n_threads, int iters, bool square) {
+    if (square)
+        k_modsqr_bench<<<(unsigned)(n_threads / 256), 256, 0, st>>>((fr*)data, iters);
+    else
+        k_modmul_bench<<<(unsigned)(n_threads / 256), 256, 0, st>>>((fr*)data, iters);
     return 1;
 }
 

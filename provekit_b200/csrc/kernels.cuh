@@ -82,7 +82,7 @@ int launch_pow_scan(cudaStream_t st, fr_arg challenge, fr_arg threshold, uint64_
                     unsigned long long* best);
 
 // microbenchmark: chains `iters` dependent Montgomery multiplications per thread; returns launches
-int launch_modmul_bench(cudaStream_t st, void* data, size_t n_threads, int iters);
+int launch_modmul_bench(cudaStream_t st, void* data, size_t n_threads, int iters, bool square);
 
 constexpr int REDUCE_MAX_BLOCKS = 1184;  // 148 SMs x 8
 

@@ -244,10 +244,11 @@ int pk_pow_solve(pk_ctx* ctx, const uint64_t challenge[4], double bits, uint64_t
     f64_to_u256(std::exp2(-(bits + 0.01)) * modulus, thr);      // PROVER_BIAS, pow.rs:6,37
     unsigned long long init = ~0ULL;
     PK_CUDA(ctx, cudaMemcpyAsync(ctx->d_best, &init, 8, cudaMemcpyHostToDevice, ctx->stream));
-    // chunk so that the expected number of chunks is ~1 and a chunk fills the machine
-    uint64_t chunk = (uint64_t)1 << 20;
-    double want = std::exp2(bits + 1.0);
-    while ((double)chunk < want && chunk < ((uint64_t)1 << 28)) chunk <<= 1;
+    // one launch covers ~8x the expected nonce; blocks above the first hit exit immediately (k_pow_scan),
+    // so the cost tracks the winning nonce, not the chunk size
+    uint64_t chunk = (uint64_t)1 << 18;
+    double want = std::exp2(bits + 3.0);
+    while ((double)chunk < want && chunk < ((uint64_t)1 << 30)) chunk <<= 1;
     for (uint64_t base = 0;; base += chunk) {
         {
             ProfScope ps(ctx, PROF_POW);
@@ -570,7 +571,14 @@ int pk_profile_end(pk_ctx* ctx, double ms_by_class[8], uint64_t launches_by_clas
 }
 
 // ---- measurement helper (not part of the reference surface) ----------------------------------------
+static int modmul_bench(pk_ctx* ctx, size_t n_threads, int iters, float* ms_out, bool square);
 int pk_modmul_bench(pk_ctx* ctx, size_t n_threads, int iters, float* ms_out) {
+    return modmul_bench(ctx, n_threads, iters, ms_out, false);
+}
+int pk_modsqr_bench(pk_ctx* ctx, size_t n_threads, int iters, float* ms_out) {
+    return modmul_bench(ctx, n_threads, iters, ms_out, true);
+}
+static int modmul_bench(pk_ctx* ctx, size_t n_threads, int iters, float* ms_out, bool square) {
     PK_CHECK(ctx, ctx && ms_out && n_threads % 256 == 0 && n_threads > 0, "modmul_bench: n_threads must be a multiple of 256");
     PK_TRY(ensure_scratch(ctx, 2 * n_threads));
     PK_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0x11, 2 * n_threads * 32, ctx->stream));
@@ -578,9 +586,9 @@ int pk_modmul_bench(pk_ctx* ctx, size_t n_threads, int iters, float* ms_out) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    launch_modmul_bench(ctx->stream, ctx->d_scratch, n_threads, 8);  // warm-up
+    launch_modmul_bench(ctx->stream, ctx->d_scratch, n_threads, 8, square);  // warm-up
     cudaEventRecord(e0, ctx->stream);
-    ctx->launches += launch_modmul_bench(ctx->stream, ctx->d_scratch, n_threads, iters);
+    ctx->launches += launch_modmul_bench(ctx->stream, ctx->d_scratch, n_threads, iters, square);
     cudaEventRecord(e1, ctx->stream);
     PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(ms_out, e0, e1);

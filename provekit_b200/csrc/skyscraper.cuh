@@ -104,15 +104,22 @@ __device__ __forceinline__ fr sky_rc(int i) {
 }
 
 // l, r canonical (< p).  Returns compress(l, r) canonical.
+// Two Feistel rounds per iteration so that (l, r) swap roles without register moves:
+//   round 2j  : r <- r + F(l) + rc[2j]      (the new left half now lives in r)
+//   round 2j+1: l <- l + F(r) + rc[2j+1]    (roles restored)
+// Both rounds of a pair use the same F (bar for pairs 3 and 5 = rounds 6,7,10,11; reference.rs:49-60).
 __device__ __forceinline__ fr sky_compress(const fr& l_in, const fr& r_in) {
     fr l = l_in, r = r_in;
 #pragma unroll 1
-    for (int i = 0; i < 18; i++) {
-        bool is_bar = (i == 6) | (i == 7) | (i == 10) | (i == 11);
-        fr f = is_bar ? sky_bar(l) : fr_mul(l, l);
-        fr nl = fr_add(fr_add(r, f), sky_rc(i));
-        r = l;
-        l = nl;
+    for (int j = 0; j < 9; j++) {
+        const bool is_bar = (j == 3) | (j == 5);
+        if (is_bar) {
+            r = fr_add(fr_add(r, sky_bar(l)), sky_rc(2 * j));
+            l = fr_add(fr_add(l, sky_bar(r)), sky_rc(2 * j + 1));
+        } else {
+            r = fr_add(fr_add(r, fr_sqr(l)), sky_rc(2 * j));
+            l = fr_add(fr_add(l, fr_sqr(r)), sky_rc(2 * j + 1));
+        }
     }
     return fr_add(l, l_in);
 }

@@ -54,6 +54,8 @@ def main():
     iters = 512
     ms = min(ctx.modmul_bench(nthreads, iters) for _ in range(3))
     out.append(dict(kernel="modmul_bench", ms=ms, gmodmul_s=nthreads * iters * 2 / ms / 1e6))
+    ms = min(ctx.modmul_bench(nthreads, iters, True) for _ in range(3))
+    out.append(dict(kernel="modsqr_bench", ms=ms, gmodsqr_s=nthreads * iters * 2 / ms / 1e6))
 
     n = 1 << m
     # compress_many on device data
