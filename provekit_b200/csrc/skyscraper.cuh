@@ -103,25 +103,82 @@ __device__ __forceinline__ fr sky_rc(int i) {
     return c;
 }
 
+// raw 256-bit a + b + c (caller guarantees no overflow)
+__device__ __forceinline__ fr add3_raw(const fr& a, const fr& b, const fr& c) {
+    fr s;
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=r"(s.v[0]), "=r"(s.v[1]), "=r"(s.v[2]), "=r"(s.v[3]), "=r"(s.v[4]), "=r"(s.v[5]), "=r"(s.v[6]), "=r"(s.v[7])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %12;\n\t"
+        "addc.cc.u32 %5, %5, %13;\n\t"
+        "addc.cc.u32 %6, %6, %14;\n\t"
+        "addc.u32 %7, %7, %15;"
+        : "+r"(s.v[0]), "+r"(s.v[1]), "+r"(s.v[2]), "+r"(s.v[3]), "+r"(s.v[4]), "+r"(s.v[5]), "+r"(s.v[6]), "+r"(s.v[7])
+        : "r"(c.v[0]), "r"(c.v[1]), "r"(c.v[2]), "r"(c.v[3]), "r"(c.v[4]), "r"(c.v[5]), "r"(c.v[6]), "r"(c.v[7]));
+    return s;
+}
+
+// Lazy reduction (the reference's reduce_partial idea, skyscraper/core/src/reduce.rs:33-55, with 2p granularity):
+// any s < 2^256 -> s - q*2p in [0, 2p + 3*2^224), q = floor(s7 / (top limb of 2p + 1)) in {0, 1, 2}.
+__device__ __forceinline__ fr sky_reduce_2p(const fr& s) {
+    const uint32_t D = 0x60c89ce6u;
+    const bool q1 = s.v[7] >= D, q2 = s.v[7] >= 2u * D;
+    // k = 0, 2p or 4p (skyscraper/core/src/constants.rs:9-16 MODULUS[2], MODULUS[4])
+    uint32_t k0 = q2 ? 0xc0000004u : (q1 ? 0xe0000002u : 0u), k1 = q2 ? 0x0f87d64fu : (q1 ? 0x87c3eb27u : 0u);
+    uint32_t k2 = q2 ? 0xe6e5c245u : (q1 ? 0xf372e122u : 0u), k3 = q2 ? 0xa0cfa121u : (q1 ? 0x5067d090u : 0u);
+    uint32_t k4 = q2 ? 0x06056174u : (q1 ? 0x0302b0bau : 0u), k5 = q2 ? 0xe14116dau : (q1 ? 0x70a08b6du : 0u);
+    uint32_t k6 = q2 ? 0x84c680a6u : (q1 ? 0xc2634053u : 0u), k7 = q2 ? 0xc19139cbu : (q1 ? 0x60c89ce5u : 0u);
+    fr d;
+    asm("sub.cc.u32 %0, %8, %16;\n\t"
+        "subc.cc.u32 %1, %9, %17;\n\t"
+        "subc.cc.u32 %2, %10, %18;\n\t"
+        "subc.cc.u32 %3, %11, %19;\n\t"
+        "subc.cc.u32 %4, %12, %20;\n\t"
+        "subc.cc.u32 %5, %13, %21;\n\t"
+        "subc.cc.u32 %6, %14, %22;\n\t"
+        "subc.u32 %7, %15, %23;"
+        : "=r"(d.v[0]), "=r"(d.v[1]), "=r"(d.v[2]), "=r"(d.v[3]), "=r"(d.v[4]), "=r"(d.v[5]), "=r"(d.v[6]), "=r"(d.v[7])
+        : "r"(s.v[0]), "r"(s.v[1]), "r"(s.v[2]), "r"(s.v[3]), "r"(s.v[4]), "r"(s.v[5]), "r"(s.v[6]), "r"(s.v[7]),
+          "r"(k0), "r"(k1), "r"(k2), "r"(k3), "r"(k4), "r"(k5), "r"(k6), "r"(k7));
+    return d;
+}
+// [0, 2p + eps) -> canonical [0, p)
+__device__ __forceinline__ fr sky_canon(const fr& x) { return fr_reduce_once(fr_reduce_once(x)); }
+
 // l, r canonical (< p).  Returns compress(l, r) canonical.
 // Two Feistel rounds per iteration so that (l, r) swap roles without register moves:
 //   round 2j  : r <- r + F(l) + rc[2j]      (the new left half now lives in r)
 //   round 2j+1: l <- l + F(r) + rc[2j+1]    (roles restored)
 // Both rounds of a pair use the same F (bar for pairs 3 and 5 = rounds 6,7,10,11; reference.rs:49-60).
+// The state is kept lazily reduced in [0, 2p + eps) like the reference does (generic.rs:81-101); only bar
+// canonicalises its input (bar.rs:17) and only the output is fully reduced.  Bounds: fr_sqr_lazy(x) < 1.84p for
+// x < 2.1p, so r + F + rc < 4.9p < 2^256.
 __device__ __forceinline__ fr sky_compress(const fr& l_in, const fr& r_in) {
     fr l = l_in, r = r_in;
 #pragma unroll 1
     for (int j = 0; j < 9; j++) {
         const bool is_bar = (j == 3) | (j == 5);
         if (is_bar) {
-            r = fr_add(fr_add(r, sky_bar(l)), sky_rc(2 * j));
-            l = fr_add(fr_add(l, sky_bar(r)), sky_rc(2 * j + 1));
+            r = sky_reduce_2p(add3_raw(r, sky_bar(sky_canon(l)), sky_rc(2 * j)));
+            l = sky_reduce_2p(add3_raw(l, sky_bar(sky_canon(r)), sky_rc(2 * j + 1)));
         } else {
-            r = fr_add(fr_add(r, fr_sqr(l)), sky_rc(2 * j));
-            l = fr_add(fr_add(l, fr_sqr(r)), sky_rc(2 * j + 1));
+            r = sky_reduce_2p(add3_raw(r, fr_sqr_lazy(l), sky_rc(2 * j)));
+            l = sky_reduce_2p(add3_raw(l, fr_sqr_lazy(r), sky_rc(2 * j + 1)));
         }
     }
-    return fr_add(l, l_in);
+    return sky_reduce(add3_raw(l, l_in, fr_zero()));
 }
 
 // provekit/common/src/skyscraper/whir.rs:20-25 on Montgomery-form field elements
