@@ -14,6 +14,25 @@ static __device__ __forceinline__ fr arg_fr(const fr_arg& a) {
     return r;
 }
 
+// Shared-memory tile of field elements in SPLIT layout: low and high 16-byte halves in two planes, so that a warp's
+// 128-bit accesses to consecutive elements are bank-conflict free (a 32-byte element stride is a 2-way conflict).
+struct SmTile {
+    uint4* lo;
+    uint4* hi;
+    __device__ __forceinline__ SmTile(uint4* base, int n_elems) : lo(base), hi(base + n_elems) {}
+    __device__ __forceinline__ fr get(int i) const {
+        uint4 a = lo[i], b = hi[i];
+        fr r;
+        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+        r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+        return r;
+    }
+    __device__ __forceinline__ void put(int i, const fr& x) const {
+        lo[i] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+        hi[i] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+    }
+};
+
 static inline int grid_for(size_t work, int threads, int max_blocks) {
     size_t b = (work + threads - 1) / threads;
     if (b < 1) b = 1;
@@ -104,47 +123,47 @@ constexpr int WAVELET_ROW_BITS = 7;    // 2^7 rows x 16 cols x 32 B = 64 KB tile
 template <bool INV>
 __global__ void __launch_bounds__(512) k_wavelet_flat(fr* a, int bits) {
     extern __shared__ uint4 smem_raw[];
-    fr* sm = reinterpret_cast<fr*>(smem_raw);
     size_t base = (size_t)blockIdx.x << bits;
     int n = 1 << bits;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = fr_load(&a[base + i]);
+    SmTile sm(smem_raw, n);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sm.put(i, fr_load(&a[base + i]));
     __syncthreads();
     for (int hb = 0; hb < bits; hb++) {
         int h = 1 << hb;
         for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
             int i = ((t >> hb) << (hb + 1)) | (t & (h - 1));
-            fr lo = sm[i], hi = sm[i + h];
-            sm[i + h] = INV ? fr_sub(hi, lo) : fr_add(hi, lo);
+            fr lo = sm.get(i), hi = sm.get(i + h);
+            sm.put(i + h, INV ? fr_sub(hi, lo) : fr_add(hi, lo));
         }
         __syncthreads();
     }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) fr_store(&a[base + i], sm[i]);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) fr_store(&a[base + i], sm.get(i));
 }
 // rows at stride 2^l elements, S row bits, 16 contiguous columns per row
 template <bool INV>
 __global__ void __launch_bounds__(512) k_wavelet_rows(fr* a, int l, int S) {
     extern __shared__ uint4 smem_raw[];
-    fr* sm = reinterpret_cast<fr*>(smem_raw);
     size_t tile = blockIdx.x;
     size_t lowgrp = tile & (((size_t)1 << (l - 4)) - 1);
     size_t hi = tile >> (l - 4);
     size_t base = (hi << (l + S)) | (lowgrp << 4);
     int rows = 1 << S;
+    SmTile sm(smem_raw, rows * 16);
     for (int idx = threadIdx.x; idx < rows * 16; idx += blockDim.x)
-        sm[idx] = fr_load(&a[base + ((size_t)(idx >> 4) << l) + (idx & 15)]);
+        sm.put(idx, fr_load(&a[base + ((size_t)(idx >> 4) << l) + (idx & 15)]));
     __syncthreads();
     for (int hb = 0; hb < S; hb++) {
         int h = 1 << hb;
         for (int t = threadIdx.x; t < (rows / 2) * 16; t += blockDim.x) {
             int k = t & 15, b = t >> 4;
             int i = ((b >> hb) << (hb + 1)) | (b & (h - 1));
-            fr lo = sm[i * 16 + k], hiv = sm[(i + h) * 16 + k];
-            sm[(i + h) * 16 + k] = INV ? fr_sub(hiv, lo) : fr_add(hiv, lo);
+            fr lo = sm.get(i * 16 + k), hiv = sm.get((i + h) * 16 + k);
+            sm.put((i + h) * 16 + k, INV ? fr_sub(hiv, lo) : fr_add(hiv, lo));
         }
         __syncthreads();
     }
     for (int idx = threadIdx.x; idx < rows * 16; idx += blockDim.x)
-        fr_store(&a[base + ((size_t)(idx >> 4) << l) + (idx & 15)], sm[idx]);
+        fr_store(&a[base + ((size_t)(idx >> 4) << l) + (idx & 15)], sm.get(idx));
 }
 int launch_wavelet(cudaStream_t st, void* a, int log_n, bool inverse) {
     int launches = 0;
@@ -213,10 +232,12 @@ struct NttPass {
     int first, last;
     size_t leaf_stride, col_offset;
 };
-__global__ void __launch_bounds__(512) k_ntt_pass(NttPass P) {
+__global__ void __launch_bounds__(256) k_ntt_pass(NttPass P) {
     extern __shared__ uint4 smem_raw[];
-    fr* sm = reinterpret_cast<fr*>(smem_raw);
     const int S = P.S, l = P.l, L = P.L;
+    SmTile sm(smem_raw, 16 << S);
+    // twiddles of this tile, staged once: stage hb (half size h = 2^hb) owns tw[h-1 .. 2h-2]
+    fr* tw = reinterpret_cast<fr*>(smem_raw + (32 << S));
     const uint32_t tile = blockIdx.x;
     const uint32_t s = tile >> (L - S);
     const uint32_t t = tile & ((1u << (L - S)) - 1u);
@@ -241,23 +262,28 @@ __global__ void __launch_bounds__(512) k_ntt_pass(NttPass P) {
         } else {
             x = fr_load(&P.in[(((size_t)s << L) + q) * 16 + k]);
         }
-        sm[idx] = x;
+        sm.put(idx, x);
+    }
+    for (int t = threadIdx.x; t < npts - 1; t += blockDim.x) {
+        int hb = 31 - __clz(t + 1);
+        int j = t + 1 - (1 << hb);
+        uint32_t e = (((uint32_t)j << l) | Lo) << (L - 1 - hb - l + P.logE);
+        fr_store(&tw[t], fr_load_nc(&P.W[(size_t)e << P.tbl_shift]));
     }
     __syncthreads();
     for (int hb = S - 1; hb >= 0; hb--) {
         const int h = 1 << hb;
-        const int esh = L - 1 - hb - l + P.logE;
+        const bool unit_twiddle = (Lo == 0) && (hb == 0);  // the only stage whose twiddle is 1 for the whole tile
         for (int bf = threadIdx.x; bf < (npts / 2) * 16; bf += blockDim.x) {
             int k = bf & 15, b = bf >> 4;
             int j = b & (h - 1);
             int i0 = ((b >> hb) << (hb + 1)) | j;
             int i1 = i0 + h;
-            uint32_t e = (((uint32_t)j << l) | Lo) << esh;
-            fr a = sm[i0 * 16 + k], bb = sm[i1 * 16 + k];
-            sm[i0 * 16 + k] = fr_add(a, bb);
+            fr a = sm.get(i0 * 16 + k), bb = sm.get(i1 * 16 + k);
+            sm.put(i0 * 16 + k, fr_add(a, bb));
             fr d = fr_sub(a, bb);
-            if (e) d = fr_mul(d, fr_load_nc(&P.W[(size_t)e << P.tbl_shift]));
-            sm[i1 * 16 + k] = d;
+            if (!unit_twiddle && (j | Lo)) d = fr_mul(d, fr_load(&tw[h - 1 + j]));
+            sm.put(i1 * 16 + k, d);
         }
         __syncthreads();
     }
@@ -267,9 +293,9 @@ __global__ void __launch_bounds__(512) k_ntt_pass(NttPass P) {
         if (P.last) {
             uint32_t tq = L ? (__brev(q) >> (32 - L)) : 0u;
             size_t row = (size_t)s + ((size_t)tq << P.logE);
-            fr_store(&P.out[row * P.leaf_stride + P.col_offset + k], sm[idx]);
+            fr_store(&P.out[row * P.leaf_stride + P.col_offset + k], sm.get(idx));
         } else {
-            fr_store(&P.out[(((size_t)s << L) + q) * 16 + k], sm[idx]);
+            fr_store(&P.out[(((size_t)s << L) + q) * 16 + k], sm.get(idx));
         }
     }
 }
@@ -283,7 +309,8 @@ int launch_rs_encode(cudaStream_t st, const void* coeffs, int log_n, int log_inv
     int done = 0;  // stage bits processed, from the top
     int npass = L == 0 ? 1 : (L + NTT_TILE_BITS - 1) / NTT_TILE_BITS;
     for (int p = 0; p < npass; p++) {
-        int S = L - done < NTT_TILE_BITS ? L - done : NTT_TILE_BITS;
+        // balanced split (17 -> 6+6+5 rather than 7+7+3): tiny tiles waste the load/store phases
+        int S = (L - done + (npass - p) - 1) / (npass - p);
         NttPass P;
         P.first = p == 0;
         P.last = p == npass - 1;
@@ -299,8 +326,8 @@ int launch_rs_encode(cudaStream_t st, const void* coeffs, int log_n, int log_inv
         P.leaf_stride = leaf_stride;
         P.col_offset = col_offset;
         unsigned grid = 1u << (logE + L - S);
-        size_t smem = (size_t)32 * 16 << S;
-        k_ntt_pass<<<grid, S >= 6 ? 512 : (S >= 4 ? 128 : 32), smem, st>>>(P);
+        size_t smem = ((size_t)32 * 16 << S) + ((size_t)32 << S);
+        k_ntt_pass<<<grid, S >= 5 ? 256 : (S >= 4 ? 128 : 32), smem, st>>>(P);
         launches++;
         done += S;
     }
@@ -735,7 +762,7 @@ cudaError_t init_kernel_attributes() {
     if ((e = cudaFuncSetAttribute(k_wavelet_flat<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
     if ((e = cudaFuncSetAttribute(k_wavelet_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
     if ((e = cudaFuncSetAttribute(k_wavelet_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
-    if ((e = cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+    if ((e = cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, smem + 4096))) return e;
     return cudaSuccess;
 }
 
