@@ -108,10 +108,15 @@ int pk_commit_open(pk_ctx *ctx, const pk_commitment *c, const uint64_t *sorted_i
 /* ---- univariate / multilinear helpers used by commit_batch and Prover::prove [whir] ---------- */
 /* OOD answer: coefficient vector evaluated at (z^(2^(n-1)),..,z^2,z) = Horner at z */
 int pk_eval_univariate(pk_ctx *ctx, const pk_buf *coeffs, size_t n, const uint64_t z[4], uint64_t out[4]);
+/* the same point for k <= 3 polynomials in one pass (commit_batch evaluates every polynomial of the batch) */
+int pk_eval_univariate_batch(pk_ctx *ctx, const pk_buf *const *coeffs, int k, size_t n, const uint64_t z[4], uint64_t *out);
 /* y[i] += a * x[i]  (batching p0 + b*p1; linear-weight accumulation) */
 int pk_axpy(pk_ctx *ctx, pk_buf *y, const pk_buf *x, const uint64_t a[4], size_t n);
 /* Weights::weighted_sum: <a, b> over n elements (call site whir_r1cs.rs:398-399) */
 int pk_dot(pk_ctx *ctx, const pk_buf *a, const pk_buf *b, size_t n, uint64_t out[4]);
+/* out[ja*nb + jb] = <a_ja, b_jb> in ONE pass; shapes (na, nb) = (3, 2) or (1, 2): the f_sums / g_sums of
+ * create_combined_statement_over_two_polynomials (whir_r1cs.rs:382-412) */
+int pk_multi_dot(pk_ctx *ctx, const pk_buf *const *a, int na, const pk_buf *const *b, int nb, size_t n, uint64_t *out);
 /* eval_eq (provekit/common/src/utils/sumcheck.rs:145-171): out[idx] += scalar * eq(point, idx),
  * point[0] <-> most significant index bit; n variables */
 int pk_eval_eq(pk_ctx *ctx, const uint64_t *point, int n, const uint64_t scalar[4], pk_buf *out);
@@ -119,6 +124,8 @@ int pk_eval_eq(pk_ctx *ctx, const uint64_t *point, int n, const uint64_t scalar[
 int pk_eval_eq_batch(pk_ctx *ctx, const uint64_t *points, size_t k, int n, const uint64_t *scalars, pk_buf *out);
 /* Weights::linear(w).compute(point): sum_idx evals[idx] * eq(point, idx) */
 int pk_mle_eval(pk_ctx *ctx, const pk_buf *evals, int log_n, const uint64_t *point, uint64_t out[4]);
+/* k <= 3 weight vectors at the same point in one pass (the deferred_weight_evaluations hint) */
+int pk_mle_eval_batch(pk_ctx *ctx, const pk_buf *const *evals, int k, int log_n, const uint64_t *point, uint64_t *out);
 /* CoefficientList::fold: 2^k consecutive coefficients -> 1; r[j] binds bit j of the in-block index */
 int pk_fold_coeffs(pk_ctx *ctx, const pk_buf *coeffs, int log_n, const uint64_t *r, int k, pk_buf *out);
 

@@ -171,6 +171,26 @@ class Context:
         self._chk(self.L.pk_eval_univariate(self.h, coeffs.h, n, _p(_fe(z)), _p(out)))
         return out
 
+    def eval_univariate_batch(self, polys, n: int, z) -> np.ndarray:
+        arr = (c_void_p * len(polys))(*[p.h for p in polys])
+        out = np.empty((len(polys), 4), np.uint64)
+        self._chk(self.L.pk_eval_univariate_batch(self.h, arr, len(polys), n, _p(_fe(z)), _p(out)))
+        return out
+
+    def multi_dot(self, a_list, b_list, n: int) -> np.ndarray:
+        """out[ja, jb] = <a_ja, b_jb> in one pass; shapes (3,2) or (1,2)."""
+        aa = (c_void_p * len(a_list))(*[p.h for p in a_list])
+        bb = (c_void_p * len(b_list))(*[p.h for p in b_list])
+        out = np.empty((len(a_list) * len(b_list), 4), np.uint64)
+        self._chk(self.L.pk_multi_dot(self.h, aa, len(a_list), bb, len(b_list), n, _p(out)))
+        return out.reshape(len(a_list), len(b_list), 4)
+
+    def mle_eval_batch(self, evals_list, log_n: int, point) -> np.ndarray:
+        arr = (c_void_p * len(evals_list))(*[p.h for p in evals_list])
+        out = np.empty((len(evals_list), 4), np.uint64)
+        self._chk(self.L.pk_mle_eval_batch(self.h, arr, len(evals_list), log_n, _p(_fe(point)), _p(out)))
+        return out
+
     def axpy(self, y: Buffer, x: Buffer, a, n: int):
         self._chk(self.L.pk_axpy(self.h, y.h, x.h, _p(_fe(a)), n))
 

@@ -291,8 +291,7 @@ int Prover::batch_commit(int m, pk_buf* masked_evals, pk_buf* g_evals, Commitmen
     fs.add_scalars(&rootf, 1);
     fs.challenge_scalars(&cm->ood_point, 1);
     Fr ans[2];
-    PK_TRY(pk_eval_univariate(ctx, *mc, N, cm->ood_point.l, ans[0].l));
-    PK_TRY(pk_eval_univariate(ctx, *gc, N, cm->ood_point.l, ans[1].l));
+    PK_TRY(pk_eval_univariate_batch(ctx, polys, 2, N, cm->ood_point.l, ans[0].l));
     fs.add_scalars(ans, 2);
     fs.challenge_scalars(&cm->batching, 1);
     PK_TRY(pk_axpy(ctx, *mc, *gc, cm->batching.l, N));  // batched polynomial p0 + b*p1
@@ -471,11 +470,9 @@ int Prover::whir_prove(const WhirCfg& cfg, Commitment* cm, pk_buf* const* weight
     for (int i = 0; i < n && i < (int)all_r.size(); i++) R[i] = all_r[all_r.size() - 1 - i];
     std::vector<uint8_t> hb;
     pkh::put_u64(hb, (uint64_t)n_weights);
-    for (int j = 0; j < n_weights; j++) {
-        Fr v;
-        PK_TRY(pk_mle_eval(ctx, weights[j], n, R[0].l, v.l));
-        pkh::put_fr(hb, v);
-    }
+    Fr dv[3];
+    PK_TRY(pk_mle_eval_batch(ctx, weights, n_weights, n, R[0].l, dv[0].l));
+    for (int j = 0; j < n_weights; j++) pkh::put_fr(hb, dv[j]);
     fs.hint(hb);
     return PK_OK;
 }
@@ -555,8 +552,9 @@ int Prover::run() {
         if (!dw.b) return pk::set_err(ctx, PK_ERR_OOM, "prove: out of device memory");
         PK_TRY(pk_buf_upload(ctx, dw, 0, wt[0].l, Nh));
         Fr fg[2];
-        PK_TRY(pk_dot(ctx, dw, masked_h, Nh, fg[0].l));
-        PK_TRY(pk_dot(ctx, dw, g_h, Nh, fg[1].l));
+        const pk_buf* wa[1] = {dw};
+        const pk_buf* fb[2] = {masked_h, g_h};
+        PK_TRY(pk_multi_dot(ctx, wa, 1, fb, 2, Nh, fg[0].l));
         Fr stmt = pkh::add(fg[0], pkh::mul(cmh.batching, fg[1]));
         fs.add_scalars(fg, 2);
         pk_buf* ws[1] = {dw};
@@ -571,12 +569,19 @@ int Prover::run() {
     PK_TRY(pk_buf_zero(ctx, eq_alpha, 0, N0));
     PK_TRY(pk_eval_eq(ctx, alpha[0].l, m0, pkh::ONE.l, eq_alpha));
     const DevCsr* T3[3] = {&P->At, &P->Bt, &P->Ct};
-    Fr f_sums[3], g_sums[3], stmts[3];
+    Fr f_sums[3], g_sums[3], stmts[3], fg6[6];
     for (int j = 0; j < 3; j++) {
         PK_TRY(pk_buf_zero(ctx, *wts[j], 0, N));
         PK_TRY(spmv(ctx, *T3[j], P->d_interned, eq_alpha.b->d, wts[j]->b->d, nw));
-        PK_TRY(pk_dot(ctx, *wts[j], masked_w, N, f_sums[j].l));
-        PK_TRY(pk_dot(ctx, *wts[j], g_w, N, g_sums[j].l));
+    }
+    {   // the weights vanish beyond the (padded) witness half: N/2 terms suffice for <w_j, f> and <w_j, g>
+        const pk_buf* wa[3] = {*wts[0], *wts[1], *wts[2]};
+        const pk_buf* fb[2] = {masked_w, g_w};
+        PK_TRY(pk_multi_dot(ctx, wa, 3, fb, 2, N / 2, fg6[0].l));
+    }
+    for (int j = 0; j < 3; j++) {
+        f_sums[j] = fg6[2 * j];
+        g_sums[j] = fg6[2 * j + 1];
         stmts[j] = pkh::add(f_sums[j], pkh::mul(cmw.batching, g_sums[j]));
     }
     T()[6] += now_s() - t0;

@@ -85,6 +85,42 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const fr* __restrict__ 
     block_reduce<NS>(acc, result);
 }
 
+static __device__ __forceinline__ fr fr_load_cg(const void* p) {  // L2 (cache-global) load: sees other blocks' stores
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldcg(q), b = __ldcg(q + 1);
+    fr r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+// Whole-grid reduction in ONE launch: every block publishes its partial sums, the block that arrives last
+// (atomic ticket) adds them up and writes `result`.  Field addition is exact, so the order does not matter.
+// The ticket counter lives right behind the partials area and is reset by the last block.
+__device__ __forceinline__ unsigned int* reduce_counter(fr* partials) {
+    return reinterpret_cast<unsigned int*>(partials + (size_t)REDUCE_MAX_BLOCKS * REDUCE_MAX_SUMS);
+}
+template <int NS>
+static __device__ __forceinline__ void grid_reduce(fr (&acc)[NS], fr* partials, fr* result) {
+    __shared__ bool is_last;
+    block_reduce<NS>(acc, &partials[(size_t)blockIdx.x * NS]);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int ticket = atomicAdd(reduce_counter(partials), 1u);
+        is_last = ticket == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    fr tot[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) tot[s] = fr_zero();
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+#pragma unroll
+        for (int s = 0; s < NS; s++) tot[s] = fr_add(tot[s], fr_load_cg(&partials[(size_t)b * NS + s]));
+    block_reduce<NS>(tot, result);
+    if (threadIdx.x == 0) *reduce_counter(partials) = 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Skyscraper compress_many  (seam: CompressManyFn)
 // ------------------------------------------------------------------------------------------------
@@ -384,11 +420,15 @@ int launch_merkle_upper(cudaStream_t st, size_t L, void* nodes) {
 // ------------------------------------------------------------------------------------------------
 // tensor-product tables (eq / power tables), accumulate, dot products
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_tensor_tables(const fr* __restrict__ points, int pt_stride, int var_off,
-                                                       int nv, const fr* __restrict__ scales, bool eq_mode, fr* out) {
-    size_t k = blockIdx.x;
-    fr* T = out + (k << nv);
-    if (threadIdx.x == 0) fr_store(&T[0], scales ? fr_load(&scales[k]) : fr_one());
+// block (2k + part): part 0 builds the high table of point k (variables [0, nv_hi), scaled), part 1 the low table
+// (variables [nv_hi, nv_hi + nv_lo))
+__global__ void __launch_bounds__(256) k_tensor_tables(const fr* __restrict__ points, int pt_stride, int nv_hi, int nv_lo,
+                                                       const fr* __restrict__ scales, bool eq_mode, fr* out_hi, fr* out_lo) {
+    const size_t k = blockIdx.x >> 1;
+    const int part = blockIdx.x & 1;
+    const int nv = part ? nv_lo : nv_hi, var_off = part ? nv_hi : 0;
+    fr* T = (part ? out_lo : out_hi) + (k << nv);
+    if (threadIdx.x == 0) fr_store(&T[0], (!part && scales) ? fr_load(&scales[k]) : fr_one());
     __syncthreads();
     int len = 1;
     for (int j = nv - 1; j >= 0; j--) {  // last variable <-> least significant index bit
@@ -403,11 +443,11 @@ __global__ void __launch_bounds__(256) k_tensor_tables(const fr* __restrict__ po
         __syncthreads();
     }
 }
-int launch_tensor_tables(cudaStream_t st, const void* points, size_t K, int pt_stride, int var_off, int nv,
-                         const void* scales, bool eq_mode, void* out) {
+int launch_tensor_tables(cudaStream_t st, const void* points, size_t K, int pt_stride, int nv_hi, int nv_lo,
+                         const void* scales, bool eq_mode, void* out_hi, void* out_lo) {
     if (K == 0) return 0;
-    k_tensor_tables<<<(unsigned)K, 256, 0, st>>>((const fr*)points, pt_stride, var_off, nv, (const fr*)scales, eq_mode,
-                                                 (fr*)out);
+    k_tensor_tables<<<(unsigned)(2 * K), 256, 0, st>>>((const fr*)points, pt_stride, nv_hi, nv_lo, (const fr*)scales, eq_mode,
+                                                     (fr*)out_hi, (fr*)out_lo);
     return 1;
 }
 __global__ void __launch_bounds__(256) k_tensor_accumulate(fr* out, size_t n, const fr* __restrict__ hi,
@@ -431,33 +471,100 @@ int launch_tensor_accumulate(cudaStream_t st, void* out, int log_n, const void* 
     return 1;
 }
 __global__ void __launch_bounds__(256) k_tensor_dot(const fr* __restrict__ a, size_t n, const fr* __restrict__ hi,
-                                                    const fr* __restrict__ lo, int lo_bits, fr* partials) {
+                                                    const fr* __restrict__ lo, int lo_bits, fr* partials, fr* result) {
     fr acc[1] = {fr_zero()};
     size_t mask = ((size_t)1 << lo_bits) - 1;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         fr t = fr_mul(fr_load_nc(&hi[i >> lo_bits]), fr_load_nc(&lo[i & mask]));
         acc[0] = fr_add(acc[0], fr_mul(fr_load_nc(&a[i]), t));
     }
-    block_reduce<1>(acc, &partials[blockIdx.x]);
+    grid_reduce<1>(acc, partials, result);
 }
 int launch_tensor_dot(cudaStream_t st, const void* a, size_t n, const void* hi, const void* lo, int lo_bits,
                       void* partials, void* result) {
     int g = grid_for(n, 256, REDUCE_MAX_BLOCKS);
-    k_tensor_dot<<<g, 256, 0, st>>>((const fr*)a, n, (const fr*)hi, (const fr*)lo, lo_bits, (fr*)partials);
-    k_reduce_partials<1><<<1, 256, 0, st>>>((const fr*)partials, g, (fr*)result);
-    return 2;
+    k_tensor_dot<<<g, 256, 0, st>>>((const fr*)a, n, (const fr*)hi, (const fr*)lo, lo_bits, (fr*)partials, (fr*)result);
+    return 1;
 }
-__global__ void __launch_bounds__(256) k_dot(const fr* __restrict__ a, const fr* __restrict__ b, size_t n, fr* partials) {
+__global__ void __launch_bounds__(256) k_dot(const fr* __restrict__ a, const fr* __restrict__ b, size_t n, fr* partials,
+                                             fr* result) {
     fr acc[1] = {fr_zero()};
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         acc[0] = fr_add(acc[0], fr_mul(fr_load_nc(&a[i]), fr_load_nc(&b[i])));
-    block_reduce<1>(acc, &partials[blockIdx.x]);
+    grid_reduce<1>(acc, partials, result);
 }
 int launch_dot(cudaStream_t st, const void* a, const void* b, size_t n, void* partials, void* result) {
     int g = grid_for(n, 256, REDUCE_MAX_BLOCKS);
-    k_dot<<<g, 256, 0, st>>>((const fr*)a, (const fr*)b, n, (fr*)partials);
-    k_reduce_partials<1><<<1, 256, 0, st>>>((const fr*)partials, g, (fr*)result);
-    return 2;
+    k_dot<<<g, 256, 0, st>>>((const fr*)a, (const fr*)b, n, (fr*)partials, (fr*)result);
+    return 1;
+}
+// result[ja * NB + jb] = <a_ja, b_jb>: one pass over NA + NB arrays instead of NA * NB dot products
+// (the six sums <w_j, f>, <w_j, g> of create_combined_statement_over_two_polynomials, whir_r1cs.rs:382-412)
+struct DotPtrs {
+    const fr* a[3];
+    const fr* b[2];
+};
+template <int NA, int NB>
+__global__ void __launch_bounds__(256) k_multi_dot(DotPtrs P, size_t n, fr* partials, fr* result) {
+    fr acc[NA * NB];
+#pragma unroll
+    for (int s = 0; s < NA * NB; s++) acc[s] = fr_zero();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        fr bv[NB];
+#pragma unroll
+        for (int jb = 0; jb < NB; jb++) bv[jb] = fr_load_nc(&P.b[jb][i]);
+#pragma unroll
+        for (int ja = 0; ja < NA; ja++) {
+            fr av = fr_load_nc(&P.a[ja][i]);
+#pragma unroll
+            for (int jb = 0; jb < NB; jb++) acc[ja * NB + jb] = fr_add(acc[ja * NB + jb], fr_mul(av, bv[jb]));
+        }
+    }
+    grid_reduce<NA * NB>(acc, partials, result);
+}
+int launch_multi_dot(cudaStream_t st, const void* const* a, int na, const void* const* b, int nb, size_t n, void* partials,
+                     void* result) {
+    DotPtrs P = {};
+    for (int i = 0; i < na; i++) P.a[i] = (const fr*)a[i];
+    for (int i = 0; i < nb; i++) P.b[i] = (const fr*)b[i];
+    int g = grid_for(n, 256, REDUCE_MAX_BLOCKS);
+    if (na == 3 && nb == 2)
+        k_multi_dot<3, 2><<<g, 256, 0, st>>>(P, n, (fr*)partials, (fr*)result);
+    else if (na == 1 && nb == 2)
+        k_multi_dot<1, 2><<<g, 256, 0, st>>>(P, n, (fr*)partials, (fr*)result);
+    else
+        return -1;
+    return 1;
+}
+// results[j] = sum_idx a_j[idx] * hi[idx >> lo_bits] * lo[idx & mask], j < NA (same tensor point for all arrays)
+template <int NA>
+__global__ void __launch_bounds__(256) k_multi_tensor_dot(DotPtrs P, size_t n, const fr* __restrict__ hi,
+                                                          const fr* __restrict__ lo, int lo_bits, fr* partials, fr* result) {
+    fr acc[NA];
+#pragma unroll
+    for (int s = 0; s < NA; s++) acc[s] = fr_zero();
+    size_t mask = ((size_t)1 << lo_bits) - 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        fr t = fr_mul(fr_load_nc(&hi[i >> lo_bits]), fr_load_nc(&lo[i & mask]));
+#pragma unroll
+        for (int ja = 0; ja < NA; ja++) acc[ja] = fr_add(acc[ja], fr_mul(fr_load_nc(&P.a[ja][i]), t));
+    }
+    grid_reduce<NA>(acc, partials, result);
+}
+int launch_multi_tensor_dot(cudaStream_t st, const void* const* a, int na, size_t n, const void* hi, const void* lo,
+                            int lo_bits, void* partials, void* result) {
+    DotPtrs P = {};
+    for (int i = 0; i < na; i++) P.a[i] = (const fr*)a[i];
+    int g = grid_for(n, 256, REDUCE_MAX_BLOCKS);
+    if (na == 1)
+        k_multi_tensor_dot<1><<<g, 256, 0, st>>>(P, n, (const fr*)hi, (const fr*)lo, lo_bits, (fr*)partials, (fr*)result);
+    else if (na == 2)
+        k_multi_tensor_dot<2><<<g, 256, 0, st>>>(P, n, (const fr*)hi, (const fr*)lo, lo_bits, (fr*)partials, (fr*)result);
+    else if (na == 3)
+        k_multi_tensor_dot<3><<<g, 256, 0, st>>>(P, n, (const fr*)hi, (const fr*)lo, lo_bits, (fr*)partials, (fr*)result);
+    else
+        return -1;
+    return 1;
 }
 __global__ void __launch_bounds__(256) k_axpy(fr* y, const fr* __restrict__ x, fr_arg a, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -503,7 +610,8 @@ int launch_fold_coeffs(cudaStream_t st, const void* coeffs, int log_n, const voi
 // the map of provekit/prover/src/whir_r1cs.rs:284-291).  MSB pairing: i <-> i + len/2.
 // ------------------------------------------------------------------------------------------------
 template <bool FOLD>
-__global__ void __launch_bounds__(256) k_zk_sumcheck(fr* a, fr* b, fr* c, fr* eq, size_t half, fr_arg foldv, fr* partials) {
+__global__ void __launch_bounds__(256) k_zk_sumcheck(fr* a, fr* b, fr* c, fr* eq, size_t half, fr_arg foldv, fr* partials,
+                                                     fr* result) {
     // `half` = (length after folding) / 2; before folding the arrays are 4*half long
     fr acc[3] = {fr_zero(), fr_zero(), fr_zero()};
     fr f = arg_fr(foldv);
@@ -534,7 +642,7 @@ __global__ void __launch_bounds__(256) k_zk_sumcheck(fr* a, fr* b, fr* c, fr* eq
         acc[1] = fr_add(acc[1], fm);
         acc[2] = fr_add(acc[2], fi);
     }
-    block_reduce<3>(acc, &partials[blockIdx.x * 3]);
+    grid_reduce<3>(acc, partials, result);
 }
 int launch_zk_sumcheck_round(cudaStream_t st, void* a, void* b, void* c, void* eq, int log_n, bool has_fold,
                              fr_arg fold, void* partials, void* result) {
@@ -542,11 +650,10 @@ int launch_zk_sumcheck_round(cudaStream_t st, void* a, void* b, void* c, void* e
     size_t half = n_after / 2;
     int g = grid_for(half, 256, REDUCE_MAX_BLOCKS);
     if (has_fold)
-        k_zk_sumcheck<true><<<g, 256, 0, st>>>((fr*)a, (fr*)b, (fr*)c, (fr*)eq, half, fold, (fr*)partials);
+        k_zk_sumcheck<true><<<g, 256, 0, st>>>((fr*)a, (fr*)b, (fr*)c, (fr*)eq, half, fold, (fr*)partials, (fr*)result);
     else
-        k_zk_sumcheck<false><<<g, 256, 0, st>>>((fr*)a, (fr*)b, (fr*)c, (fr*)eq, half, fold, (fr*)partials);
-    k_reduce_partials<3><<<1, 256, 0, st>>>((const fr*)partials, g, (fr*)result);
-    return 2;
+        k_zk_sumcheck<false><<<g, 256, 0, st>>>((fr*)a, (fr*)b, (fr*)c, (fr*)eq, half, fold, (fr*)partials, (fr*)result);
+    return 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -554,7 +661,8 @@ int launch_zk_sumcheck_round(cudaStream_t st, void* a, void* b, void* c, void* e
 // ------------------------------------------------------------------------------------------------
 template <bool FOLD>
 __global__ void __launch_bounds__(256) k_whir_sumcheck(const fr* __restrict__ p_in, const fr* __restrict__ w_in,
-                                                       fr* p_out, fr* w_out, size_t pairs, fr_arg foldv, fr* partials) {
+                                                       fr* p_out, fr* w_out, size_t pairs, fr_arg foldv, fr* partials,
+                                                       fr* result) {
     fr acc[3] = {fr_zero(), fr_zero(), fr_zero()};
     fr f = arg_fr(foldv);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (size_t)gridDim.x * blockDim.x) {
@@ -580,7 +688,7 @@ __global__ void __launch_bounds__(256) k_whir_sumcheck(const fr* __restrict__ p_
         acc[1] = fr_add(acc[1], fr_mul(p1, w1));
         acc[2] = fr_add(acc[2], fr_mul(fr_sub(fr_dbl(p1), p0), fr_sub(fr_dbl(w1), w0)));
     }
-    block_reduce<3>(acc, &partials[blockIdx.x * 3]);
+    grid_reduce<3>(acc, partials, result);
 }
 int launch_whir_sumcheck_round(cudaStream_t st, const void* p_in, const void* w_in, void* p_out, void* w_out,
                                int log_n, bool has_fold, fr_arg fold, void* partials, void* result) {
@@ -589,12 +697,11 @@ int launch_whir_sumcheck_round(cudaStream_t st, const void* p_in, const void* w_
     int g = grid_for(pairs, 256, REDUCE_MAX_BLOCKS);
     if (has_fold)
         k_whir_sumcheck<true><<<g, 256, 0, st>>>((const fr*)p_in, (const fr*)w_in, (fr*)p_out, (fr*)w_out, pairs, fold,
-                                                 (fr*)partials);
+                                                 (fr*)partials, (fr*)result);
     else
         k_whir_sumcheck<false><<<g, 256, 0, st>>>((const fr*)p_in, (const fr*)w_in, (fr*)p_out, (fr*)w_out, pairs, fold,
-                                                  (fr*)partials);
-    k_reduce_partials<3><<<1, 256, 0, st>>>((const fr*)partials, g, (fr*)result);
-    return 2;
+                                                  (fr*)partials, (fr*)result);
+    return 1;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -33,11 +33,12 @@ int launch_rs_encode(cudaStream_t st, const void* coeffs, int log_n, int log_inv
 int launch_merkle_leaves(cudaStream_t st, const void* leaves, size_t L, size_t w, void* nodes);
 int launch_merkle_upper(cudaStream_t st, size_t L, void* nodes);
 
-// tensor-product tables: for point k (k < K) and variable j (j < nv, point[k*pt_stride + var_off + j]):
-//   T_k[idx] = scale_k * prod_j (bit_{nv-1-j}(idx) ? f1 : f0),   eq: (f0,f1) = (1-x, x);  pow: (1, x)
-// scales may be null (=1).  out: K tables of 2^nv.
-int launch_tensor_tables(cudaStream_t st, const void* points, size_t K, int pt_stride, int var_off, int nv,
-                         const void* scales, bool eq_mode, void* out);
+// tensor-product tables of K points with nv_hi + nv_lo variables each (point k at points[k*pt_stride ..]):
+//   hi_k[idx] = scale_k * prod_{j < nv_hi} (bit_{nv_hi-1-j}(idx) ? f1 : f0)   over the first nv_hi variables,
+//   lo_k[idx] =           prod over the remaining nv_lo variables;            eq: (f0,f1) = (1-x, x);  pow: (1, x)
+// so that T_k[idx] = hi_k[idx >> nv_lo] * lo_k[idx & mask].  scales may be null (= 1).  One launch builds both.
+int launch_tensor_tables(cudaStream_t st, const void* points, size_t K, int pt_stride, int nv_hi, int nv_lo,
+                         const void* scales, bool eq_mode, void* out_hi, void* out_lo);
 // out[idx] += sum_k hi_k[idx >> lo_bits] * lo_k[idx & mask]
 int launch_tensor_accumulate(cudaStream_t st, void* out, int log_n, const void* hi, const void* lo, size_t K,
                              int lo_bits);
@@ -46,6 +47,11 @@ int launch_tensor_dot(cudaStream_t st, const void* a, size_t n, const void* hi, 
                       void* partials, void* result);
 // result[0] = <a, b>
 int launch_dot(cudaStream_t st, const void* a, const void* b, size_t n, void* partials, void* result);
+// result[ja*nb + jb] = <a_ja, b_jb>  ((na, nb) in {(3,2), (1,2)});  result[j] = sum a_j[i] * (hi (x) lo)[i], na <= 3
+int launch_multi_dot(cudaStream_t st, const void* const* a, int na, const void* const* b, int nb, size_t n, void* partials,
+                     void* result);
+int launch_multi_tensor_dot(cudaStream_t st, const void* const* a, int na, size_t n, const void* hi, const void* lo,
+                            int lo_bits, void* partials, void* result);
 int launch_axpy(cudaStream_t st, void* y, const void* x, fr_arg a, size_t n);
 int launch_fold_coeffs(cudaStream_t st, const void* coeffs, int log_n, const void* r_dev, int k, void* out);
 
@@ -85,5 +91,8 @@ int launch_pow_scan(cudaStream_t st, fr_arg challenge, fr_arg threshold, uint64_
 int launch_modmul_bench(cudaStream_t st, void* data, size_t n_threads, int iters, bool square);
 
 constexpr int REDUCE_MAX_BLOCKS = 1184;  // 148 SMs x 8
+constexpr int REDUCE_MAX_SUMS = 6;       // field sums per reduction kernel
+// bytes of the partials work area: per-block partial sums + the ticket counter of the single-launch reduction
+constexpr size_t REDUCE_AREA_BYTES = (size_t)REDUCE_MAX_BLOCKS * REDUCE_MAX_SUMS * 32 + 64;
 
 }  // namespace pk

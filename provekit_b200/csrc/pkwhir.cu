@@ -91,7 +91,8 @@ int pk_ctx_create(int device, pk_ctx** out) {
     pk_ctx* ctx = new pk_ctx();
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&ctx->d_partials, (size_t)REDUCE_MAX_BLOCKS * 3 * 32) != cudaSuccess ||
+        cudaMalloc(&ctx->d_partials, REDUCE_AREA_BYTES) != cudaSuccess ||
+        cudaMemset(ctx->d_partials, 0, REDUCE_AREA_BYTES) != cudaSuccess ||
         cudaMalloc(&ctx->d_result, 64 * 32) != cudaSuccess || cudaMallocHost((void**)&ctx->h_result, 64 * 32) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_best, 8) != cudaSuccess || init_kernel_attributes() != cudaSuccess) {
         pk_ctx_destroy(ctx);
@@ -421,11 +422,28 @@ int pk_commit_open(pk_ctx* ctx, const pk_commitment* c, const uint64_t* sorted_i
 // ---- univariate / multilinear helpers ------------------------------------------------------------
 static int split_bits(int n) { return n / 2; }  // low-table bits
 
-int pk_eval_univariate(pk_ctx* ctx, const pk_buf* coeffs, size_t n, const uint64_t z[4], uint64_t out[4]) {
-    PK_CHECK(ctx, coeffs && z && out && n >= 1 && (n & (n - 1)) == 0 && coeffs->n >= n, "eval_univariate: bad arguments");
+// tables for (hi, lo) halves of `point` (nv variables) into ctx->d_tables; returns pointers and the split
+static int build_point_tables(pk_ctx* ctx, const uint64_t* point, int nv, bool eq_mode, char** t_hi, char** t_lo, int* lo_bits) {
+    int lo = split_bits(nv), hi = nv - lo;
+    PK_TRY(ensure_small(ctx, (size_t)(nv + 1) * 32));
+    PK_TRY(ensure_tables(ctx, ((size_t)1 << lo) + ((size_t)1 << hi)));
+    if (nv > 0) PK_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, point, (size_t)nv * 32, cudaMemcpyHostToDevice, ctx->stream));
+    *t_hi = (char*)ctx->d_tables;
+    *t_lo = *t_hi + ((size_t)32 << hi);
+    *lo_bits = lo;
+    ctx->launches += launch_tensor_tables(ctx->stream, ctx->d_small, 1, nv, hi, lo, nullptr, eq_mode, *t_hi, *t_lo);
+    return PK_OK;
+}
+int pk_eval_univariate_batch(pk_ctx* ctx, const pk_buf* const* coeffs, int k, size_t n, const uint64_t z[4], uint64_t* out) {
+    PK_CHECK(ctx, coeffs && z && out && k >= 1 && k <= 3 && n >= 1 && (n & (n - 1)) == 0, "eval_univariate: bad arguments");
+    const void* ptrs[3] = {nullptr, nullptr, nullptr};
+    for (int j = 0; j < k; j++) {
+        PK_CHECK(ctx, coeffs[j] && coeffs[j]->n >= n, "eval_univariate: polynomial %d too small", j);
+        ptrs[j] = coeffs[j]->d;
+    }
     int nv = 0;
     while (((size_t)1 << nv) < n) nv++;
-    // point (z^(2^(nv-1)), ..., z^2, z) : power tables instead of eq tables
+    // point (z^(2^(nv-1)), ..., z^2, z): power tables instead of eq tables
     std::vector<pkh::Fr> pt(nv > 0 ? nv : 1);
     pkh::Fr acc;
     std::memcpy(acc.l, z, 32);
@@ -433,16 +451,14 @@ int pk_eval_univariate(pk_ctx* ctx, const pk_buf* coeffs, size_t n, const uint64
         pt[nv - 1 - i] = acc;
         acc = pkh::sqr(acc);
     }
-    int lo = split_bits(nv), hi = nv - lo;
-    PK_TRY(ensure_small(ctx, (size_t)(nv + 1) * 32));
-    PK_TRY(ensure_tables(ctx, ((size_t)1 << lo) + ((size_t)1 << hi)));
-    PK_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, pt.data(), (size_t)nv * 32, cudaMemcpyHostToDevice, ctx->stream));
-    char* t_hi = (char*)ctx->d_tables;
-    char* t_lo = t_hi + ((size_t)32 << hi);
-    ctx->launches += launch_tensor_tables(ctx->stream, ctx->d_small, 1, nv, 0, hi, nullptr, false, t_hi);
-    ctx->launches += launch_tensor_tables(ctx->stream, ctx->d_small, 1, nv, hi, lo, nullptr, false, t_lo);
-    ctx->launches += launch_tensor_dot(ctx->stream, coeffs->d, n, t_hi, t_lo, lo, ctx->d_partials, ctx->d_result);
-    return fetch_result(ctx, out, 1);
+    char *t_hi, *t_lo;
+    int lo;
+    PK_TRY(build_point_tables(ctx, pt[0].l, nv, false, &t_hi, &t_lo, &lo));
+    ctx->launches += launch_multi_tensor_dot(ctx->stream, ptrs, k, n, t_hi, t_lo, lo, ctx->d_partials, ctx->d_result);
+    return fetch_result(ctx, out, k);  // also orders the pageable `pt` upload before we return
+}
+int pk_eval_univariate(pk_ctx* ctx, const pk_buf* coeffs, size_t n, const uint64_t z[4], uint64_t out[4]) {
+    return pk_eval_univariate_batch(ctx, &coeffs, 1, n, z, out);
 }
 int pk_axpy(pk_ctx* ctx, pk_buf* y, const pk_buf* x, const uint64_t a[4], size_t n) {
     PK_CHECK(ctx, y && x && a && y->n >= n && x->n >= n, "axpy: buffer too small");
@@ -454,6 +470,20 @@ int pk_dot(pk_ctx* ctx, const pk_buf* a, const pk_buf* b, size_t n, uint64_t out
     PK_CHECK(ctx, a && b && out && a->n >= n && b->n >= n && n >= 1, "dot: buffer too small");
     ctx->launches += launch_dot(ctx->stream, a->d, b->d, n, ctx->d_partials, ctx->d_result);
     return fetch_result(ctx, out, 1);
+}
+int pk_multi_dot(pk_ctx* ctx, const pk_buf* const* a, int na, const pk_buf* const* b, int nb, size_t n, uint64_t* out) {
+    PK_CHECK(ctx, a && b && out && n >= 1 && ((na == 3 && nb == 2) || (na == 1 && nb == 2)), "multi_dot: unsupported shape");
+    const void *pa[3] = {nullptr, nullptr, nullptr}, *pb[2] = {nullptr, nullptr};
+    for (int i = 0; i < na; i++) {
+        PK_CHECK(ctx, a[i] && a[i]->n >= n, "multi_dot: a[%d] too small", i);
+        pa[i] = a[i]->d;
+    }
+    for (int i = 0; i < nb; i++) {
+        PK_CHECK(ctx, b[i] && b[i]->n >= n, "multi_dot: b[%d] too small", i);
+        pb[i] = b[i]->d;
+    }
+    ctx->launches += launch_multi_dot(ctx->stream, pa, na, pb, nb, n, ctx->d_partials, ctx->d_result);
+    return fetch_result(ctx, out, na * nb);
 }
 int pk_eval_eq_batch(pk_ctx* ctx, const uint64_t* points, size_t k, int n, const uint64_t* scalars, pk_buf* out) {
     PK_CHECK(ctx, points && scalars && out && n >= 0 && n < 40 && out->n >= ((size_t)1 << n), "eval_eq: bad arguments");
@@ -468,8 +498,7 @@ int pk_eval_eq_batch(pk_ctx* ctx, const uint64_t* points, size_t k, int n, const
     PK_CUDA(ctx, cudaMemcpyAsync(d_sc, scalars, sc_bytes, cudaMemcpyHostToDevice, ctx->stream));
     char* t_hi = (char*)ctx->d_tables;
     char* t_lo = t_hi + k * ((size_t)32 << hi);
-    ctx->launches += launch_tensor_tables(ctx->stream, d_pts, k, n, 0, hi, d_sc, true, t_hi);
-    ctx->launches += launch_tensor_tables(ctx->stream, d_pts, k, n, hi, lo, nullptr, true, t_lo);
+    ctx->launches += launch_tensor_tables(ctx->stream, d_pts, k, n, hi, lo, d_sc, true, t_hi, t_lo);
     ctx->launches += launch_tensor_accumulate(ctx->stream, out->d, n, t_hi, t_lo, k, lo);
     PK_CUDA(ctx, cudaGetLastError());
     // the host arrays may be reused by the caller right away
@@ -479,18 +508,21 @@ int pk_eval_eq_batch(pk_ctx* ctx, const uint64_t* points, size_t k, int n, const
 int pk_eval_eq(pk_ctx* ctx, const uint64_t* point, int n, const uint64_t scalar[4], pk_buf* out) {
     return pk_eval_eq_batch(ctx, point, 1, n, scalar, out);
 }
+int pk_mle_eval_batch(pk_ctx* ctx, const pk_buf* const* evals, int k, int log_n, const uint64_t* point, uint64_t* out) {
+    PK_CHECK(ctx, evals && point && out && k >= 1 && k <= 3 && log_n >= 0 && log_n < 40, "mle_eval: bad arguments");
+    const void* ptrs[3] = {nullptr, nullptr, nullptr};
+    for (int j = 0; j < k; j++) {
+        PK_CHECK(ctx, evals[j] && evals[j]->n >= ((size_t)1 << log_n), "mle_eval: array %d too small", j);
+        ptrs[j] = evals[j]->d;
+    }
+    char *t_hi, *t_lo;
+    int lo;
+    PK_TRY(build_point_tables(ctx, point, log_n, true, &t_hi, &t_lo, &lo));
+    ctx->launches += launch_multi_tensor_dot(ctx->stream, ptrs, k, (size_t)1 << log_n, t_hi, t_lo, lo, ctx->d_partials, ctx->d_result);
+    return fetch_result(ctx, out, k);
+}
 int pk_mle_eval(pk_ctx* ctx, const pk_buf* evals, int log_n, const uint64_t* point, uint64_t out[4]) {
-    PK_CHECK(ctx, evals && point && out && log_n >= 0 && log_n < 40 && evals->n >= ((size_t)1 << log_n), "mle_eval: bad arguments");
-    int lo = split_bits(log_n), hi = log_n - lo;
-    PK_TRY(ensure_small(ctx, (size_t)(log_n + 1) * 32));
-    PK_TRY(ensure_tables(ctx, ((size_t)1 << lo) + ((size_t)1 << hi)));
-    if (log_n > 0) PK_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, point, (size_t)log_n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    char* t_hi = (char*)ctx->d_tables;
-    char* t_lo = t_hi + ((size_t)32 << hi);
-    ctx->launches += launch_tensor_tables(ctx->stream, ctx->d_small, 1, log_n, 0, hi, nullptr, true, t_hi);
-    ctx->launches += launch_tensor_tables(ctx->stream, ctx->d_small, 1, log_n, hi, lo, nullptr, true, t_lo);
-    ctx->launches += launch_tensor_dot(ctx->stream, evals->d, (size_t)1 << log_n, t_hi, t_lo, lo, ctx->d_partials, ctx->d_result);
-    return fetch_result(ctx, out, 1);
+    return pk_mle_eval_batch(ctx, &evals, 1, log_n, point, out);
 }
 int pk_fold_coeffs(pk_ctx* ctx, const pk_buf* coeffs, int log_n, const uint64_t* r, int k, pk_buf* out) {
     PK_CHECK(ctx, coeffs && r && out && k >= 0 && k <= 4 && log_n >= k && log_n < 40, "fold_coeffs: bad arguments");

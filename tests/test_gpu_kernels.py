@@ -301,3 +301,43 @@ def test_whir_sumcheck_all_rounds(ctx, orc, log_n):
     for a, b in bufs:
         a.free()
         b.free()
+
+
+@pytest.mark.parametrize("log_n", [3, 12, 17])
+def test_batched_helpers(ctx, orc, log_n):
+    """pk_eval_univariate_batch / pk_multi_dot / pk_mle_eval_batch == the single-array oracle calls."""
+    n = 1 << log_n
+    arrs = [rng_fr(100 * log_n + k, n) for k in range(5)]
+    dev = [ctx.upload(a) for a in arrs]
+    z = rng_fr(5, 1)
+    exp = np.zeros(4, np.uint64)
+    got = ctx.eval_univariate_batch(dev[:2], n, z)
+    for j in range(2):
+        orc.orc_eval_univariate(ptr(arrs[j]), sz(n), ptr(z), ptr(exp))
+        assert np.array_equal(got[j], exp)
+    for na in (3, 1):
+        got = ctx.multi_dot(dev[:na], dev[3:5], n)
+        for ja in range(na):
+            for jb in range(2):
+                orc.orc_dot(ptr(arrs[ja]), ptr(arrs[3 + jb]), sz(n), ptr(exp))
+                assert np.array_equal(got[ja, jb], exp)
+    pt = rng_fr(9, log_n)
+    got = ctx.mle_eval_batch(dev[:3], log_n, pt)
+    for j in range(3):
+        orc.orc_mle_eval(ptr(arrs[j]), log_n, ptr(pt), ptr(exp))
+        assert np.array_equal(got[j], exp)
+    for d in dev:
+        d.free()
+
+
+def test_reductions_repeatable(ctx, orc):
+    """The single-launch grid reduction resets its ticket counter: many back-to-back reductions stay exact."""
+    n = 1 << 16
+    a, b = rng_fr(1, n), rng_fr(2, n)
+    da, db = ctx.upload(a), ctx.upload(b)
+    exp = np.zeros(4, np.uint64)
+    orc.orc_dot(ptr(a), ptr(b), sz(n), ptr(exp))
+    for _ in range(50):
+        assert np.array_equal(ctx.dot(da, db, n), exp)
+    da.free()
+    db.free()
