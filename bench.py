@@ -163,6 +163,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="poseidon-1000", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--in-flight", type=int, default=2,
+                    help="independent proofs in flight per GPU (own ctx/stream/host thread each): the host<->device "
+                         "round trips of one proof (~120 challenges) are hidden behind the kernels of the other")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 3:
@@ -172,26 +175,17 @@ def main():
 
     import torch
     import provekit_b200 as pk
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from tools.dist_util import Dist, aggregate_throughput
+    dd = Dist()
+    rank, world, local_rank = dd.rank, dd.world, dd.local_rank
     torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dist = dd.dist
 
     def barrier():
-        if dist is not None:
-            dist.barrier()
+        dd.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    max_over_ranks = dd.max
 
     r1cs = wl.synth_r1cs(**WORKLOADS[args.workload], seed=1 + rank)
     rnd = wl.randomness(r1cs, seed=7 + rank)
@@ -209,22 +203,58 @@ def main():
         rnd_p[k], t_ = pin(v)
         keep.append(t_)
 
-    ctx = pk.Context(local_rank)
-    prover = pk.Prover(ctx, r1cs)
-    stream = torch.cuda.ExternalStream(ctx.stream)
+    n_fl = max(1, args.in_flight)
+    ctxs = [pk.Context(local_rank) for _ in range(n_fl)]
+    provers = [pk.Prover(c, r1cs) for c in ctxs]
+    streams = [torch.cuda.ExternalStream(c.stream) for c in ctxs]
+    ctx, prover, stream = ctxs[0], provers[0], streams[0]
     h2d = 32 * (r1cs["num_witnesses"] + sum(len(v) for v in rnd.values()))
 
     proof = None
     for _ in range(args.warmup):
-        proof = prover.prove(witness, rnd_p)
+        for p_ in provers:
+            proof = p_.prove(witness, rnd_p)
     d2h = len(proof) + 32 * (3 * (m0 + 4 * 12) + 64)  # transcript + per-round result scalars (approx.)
 
-    # ---- device-resident arm: inputs staged once, K proofs from HBM ----
-    prover.upload_inputs(witness, rnd_p)
-    prover.prove_staged()
+    def run_concurrent(fn, steps):
+        """`steps` proofs spread over the in-flight workers; device time from an event on stream 0 before the
+        first launch to an event after every stream has drained (stream 0 waits on the others)."""
+        per = [steps // n_fl + (1 if i < steps % n_fl else 0) for i in range(n_fl)]
+        results = [None] * n_fl
+
+        def work(i):
+            for _ in range(per[i]):
+                results[i] = fn(provers[i])
+
+        for c in ctxs:
+            c.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        t0 = time.perf_counter()
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(1, n_fl)]
+        for t in threads:
+            t.start()
+        work(0)
+        for t in threads:
+            t.join()
+        for i in range(1, n_fl):
+            ev = torch.cuda.Event()
+            ev.record(streams[i])
+            stream.wait_event(ev)
+        e1.record(stream)
+        for c in ctxs:
+            c.sync()
+        wall = (time.perf_counter() - t0) * 1e3
+        return max(e0.elapsed_time(e1), 0.0), wall, results[0]
+
+    # ---- device-resident arm: inputs staged once per worker, K proofs from HBM ----
+    for p_ in provers:
+        p_.upload_inputs(witness, rnd_p)
+        p_.prove_staged()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
+    # (a) one proof at a time with per-kernel CUDA events: kernel durations for the roofline
     launches0 = ctx.launches
     ctx._chk(ctx.L.pk_profile_begin(ctx.h))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -237,23 +267,22 @@ def main():
     n_cls = (ctypes.c_uint64 * 8)()
     max_cls = (ctypes.c_double * 8)()
     ctx._chk(ctx.L.pk_profile_end(ctx.h, ms_cls, n_cls, max_cls))
-    dev_ms = e0.elapsed_time(e1)
-    barrier()
+    single_ms = e0.elapsed_time(e1)
     launches = ctx.launches - launches0
-    dev_ms = max_over_ranks(dev_ms)
     stage_t = prover.timings()
+    # (b) the measured configuration: n_fl proofs in flight
+    barrier()
+    if n_fl > 1:
+        dev_ms, dev_wall, _ = run_concurrent(lambda p_: p_.prove_staged(), args.steps)
+    else:
+        dev_ms = single_ms
+    barrier()
+    dev_ms = max_over_ranks(dev_ms)
+    single_ms = max_over_ranks(single_ms)
 
     # ---- e2e arm: host buffers in, transcript out, every step ----
     barrier()
-    t0 = time.perf_counter()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record(stream)
-    for _ in range(args.steps):
-        proof = prover.prove(witness, rnd_p)
-    e3.record(stream)
-    ctx.sync()
-    e2e_ms = e2.elapsed_time(e3)
-    e2e_wall = (time.perf_counter() - t0) * 1e3
+    e2e_ms, e2e_wall, proof = run_concurrent(lambda p_: p_.prove(witness, rnd_p), args.steps)
     barrier()
     e2e_ms = max_over_ranks(max(e2e_ms, e2e_wall))
     clocks = sampler.finish()
@@ -261,9 +290,11 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak()
         line = base_line(args, args.workload, r1cs)
-        value = world * args.steps / (dev_ms / 1e3)
-        line.update({"value": value, "ms_per_step": dev_ms / args.steps, "gpu_launches": int(launches), "clocks": clocks,
-                     "e2e": {"value": world * args.steps / (e2e_ms / 1e3), "unit": "proofs/s", "h2d_bytes_per_step": int(h2d),
+        value = aggregate_throughput(args.steps, world, dev_ms)
+        line["config"]["in_flight_proofs_per_gpu"] = n_fl
+        line.update({"value": value, "ms_per_step": dev_ms / args.steps, "ms_per_step_one_in_flight": single_ms / args.steps,
+                     "gpu_launches": int(launches), "clocks": clocks,
+                     "e2e": {"value": aggregate_throughput(args.steps, world, e2e_ms), "unit": "proofs/s", "h2d_bytes_per_step": int(h2d),
                              "d2h_bytes_per_step": int(d2h)}})
         # roofline of the dominant kernel: Merkle leaf hashing of the witness commitment (L = 2^(m-3) leaves of 32)
         L = 1 << (m + 1 - 4)
@@ -304,10 +335,11 @@ def main():
                                               "reference algorithms with OpenMP",
                                     "proof_matches_gpu": bool(cpu_proof == proof)}
         print(json.dumps(line))
-    prover.close()
-    ctx.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    for p_ in provers:
+        p_.close()
+    for c in ctxs:
+        c.close()
+    dd.close()
     return 0
 
 
