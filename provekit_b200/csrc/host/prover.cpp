@@ -693,6 +693,7 @@ void free_csr(DevCsr& c) {
 extern "C" {
 
 int pk_prover_create(pk_ctx* ctx, const pk_r1cs* r1cs, pk_prover** out) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, ctx && r1cs && out, "prover_create: null argument");
     *out = nullptr;
     PK_CHECK(ctx, r1cs->num_constraints >= 2 && r1cs->num_witnesses >= 1 && r1cs->interned, "prover_create: empty R1CS");
@@ -722,6 +723,7 @@ int pk_prover_create(pk_ctx* ctx, const pk_r1cs* r1cs, pk_prover** out) {
 }
 void pk_prover_destroy(pk_prover* p) {
     if (!p) return;
+    PK_BIND(p->ctx);
     cudaStreamSynchronize(p->ctx->stream);
     cudaFree(p->d_interned);
     pk_buf_free(p->ctx, p->masked_w);
@@ -739,6 +741,7 @@ void pk_prover_destroy(pk_prover* p) {
 int pk_prover_upload_inputs(pk_prover* p, const uint64_t* witness, const pk_rand* rnd) {
     if (!p) return PK_ERR_INVALID_ARG;
     pk_ctx* ctx = p->ctx;
+    PK_BIND(ctx);
     PK_CHECK(ctx, witness && rnd, "upload_inputs: null argument");
     PK_CHECK(ctx, rnd->mask_w && rnd->g_w && rnd->blind && rnd->mask_h && rnd->g_h, "upload_inputs: null randomness");
     const size_t half = (size_t)1 << (p->m - 1), N = (size_t)1 << p->m;
@@ -771,6 +774,7 @@ int pk_prover_upload_inputs(pk_prover* p, const uint64_t* witness, const pk_rand
 int pk_prove_staged(pk_prover* p, uint8_t** out, size_t* out_len) {
     if (!p) return PK_ERR_INVALID_ARG;
     pk_ctx* ctx = p->ctx;
+    PK_BIND(ctx);
     PK_CHECK(ctx, out && out_len, "prove: null argument");
     PK_CHECK(ctx, p->staged, "prove_staged: call pk_prover_upload_inputs first");
     double keep1 = p->timings[1];

@@ -228,8 +228,10 @@ int launch_wavelet(cudaStream_t st, void* a, int log_n, bool inverse) {
 // ------------------------------------------------------------------------------------------------
 // twiddle table: W[e] = omega^e, omega = 2-adic root of order 2^log_m; pow2[b] = omega^(2^b) from host
 // ------------------------------------------------------------------------------------------------
-__constant__ uint32_t TW_POW2[28][8];
-__global__ void k_twiddle_table(fr* table, int log_m) {
+struct TwPow2 {
+    uint32_t v[28][8];  // omega^(2^b), Montgomery form; passed by value (kernel parameter space): no device-global state
+};
+__global__ void k_twiddle_table(fr* table, int log_m, TwPow2 pw) {
     size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t n = (size_t)1 << (log_m - 1);
     if (e >= n) return;
@@ -238,19 +240,18 @@ __global__ void k_twiddle_table(fr* table, int log_m) {
         if ((e >> b) & 1) {
             fr w;
 #pragma unroll
-            for (int k = 0; k < 8; k++) w.v[k] = TW_POW2[b][k];
+            for (int k = 0; k < 8; k++) w.v[k] = pw.v[b][k];
             acc = fr_mul(acc, w);
         }
     fr_store(&table[e], acc);
 }
-// host supplies omega^(2^b) for b = 0..log_m-2 via cudaMemcpyToSymbol before calling (pkwhir.cu)
-cudaError_t set_twiddle_pow2(const uint32_t* host_pow2, int count) {
-    return cudaMemcpyToSymbol(TW_POW2, host_pow2, (size_t)count * 32);
-}
-int launch_twiddle_table(cudaStream_t st, void* table, int log_m) {
+int launch_twiddle_table(cudaStream_t st, void* table, int log_m, const uint32_t* host_pow2) {
     if (log_m < 1) return 0;
+    TwPow2 pw;
+    for (int b = 0; b < 28; b++)
+        for (int k = 0; k < 8; k++) pw.v[b][k] = host_pow2[b * 8 + k];
     size_t n = (size_t)1 << (log_m - 1);
-    k_twiddle_table<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((fr*)table, log_m);
+    k_twiddle_table<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((fr*)table, log_m, pw);
     return 1;
 }
 

@@ -22,7 +22,8 @@ int launch_to_mont(cudaStream_t st, void* data, size_t n, bool to_mont);
 int launch_wavelet(cudaStream_t st, void* a, int log_n, bool inverse);
 
 // twiddle table W[e] = omega_M^e (Montgomery), e < M/2, omega_M = arkworks 2-adic root of order M = 2^log_m
-int launch_twiddle_table(cudaStream_t st, void* table, int log_m);
+// host_pow2: 28 x 8 limbs, omega^(2^b) for b = 0..27 (Montgomery)
+int launch_twiddle_table(cudaStream_t st, void* table, int log_m, const uint32_t* host_pow2);
 
 // K1 RS encode: coeffs (2^log_n) -> out[(row)*leaf_stride + col_offset + k]; scratch: 2^(log_n+log_inv_rate)
 // table: twiddles for M = 2^(log_n + log_inv_rate - fold), table_log_m >= that (strided use)

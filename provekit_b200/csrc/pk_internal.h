@@ -87,7 +87,6 @@ int ensure_scratch(pk_ctx* ctx, size_t elems);
 int ensure_tables(pk_ctx* ctx, size_t elems);
 int ensure_small(pk_ctx* ctx, size_t bytes);
 int ensure_stage(pk_ctx* ctx, size_t bytes);
-cudaError_t set_twiddle_pow2(const uint32_t* host_pow2, int count);
 cudaError_t init_kernel_attributes();
 inline fr_arg to_arg(const uint64_t x[4]) {
     fr_arg a;
@@ -99,6 +98,11 @@ inline fr_arg to_arg(const uint64_t x[4]) {
 }
 }  // namespace pk
 
+// CUDA's current device is per host thread: every entry point binds the calling thread to the ctx's device
+#define PK_BIND(ctx)                                   \
+    do {                                               \
+        if (ctx) cudaSetDevice((ctx)->device);         \
+    } while (0)
 #define PK_CUDA(ctx, call)                                                                          \
     do {                                                                                            \
         cudaError_t e__ = (call);                                                                   \

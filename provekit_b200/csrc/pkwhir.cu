@@ -60,8 +60,7 @@ int ensure_twiddles(pk_ctx* ctx, int log_m) {
         std::memcpy(pow2[b], g.l, 32);
         g = pkh::sqr(g);
     }
-    PK_CUDA(ctx, set_twiddle_pow2(&pow2[0][0], 28));
-    ctx->launches += launch_twiddle_table(ctx->stream, ctx->d_twiddles, log_m);
+    ctx->launches += launch_twiddle_table(ctx->stream, ctx->d_twiddles, log_m, &pow2[0][0]);
     PK_CUDA(ctx, cudaGetLastError());
     ctx->twiddle_log_m = log_m;
     return PK_OK;
@@ -109,6 +108,7 @@ int pk_ctx_create(int device, pk_ctx** out) {
     return PK_OK;
 }
 void pk_ctx_destroy(pk_ctx* ctx) {
+    PK_BIND(ctx);
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -129,6 +129,7 @@ const char* pk_last_error(const pk_ctx* ctx) { return ctx ? ctx->err.c_str() : "
 uint64_t pk_launch_count(const pk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 void* pk_ctx_stream(pk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int pk_ctx_sync(pk_ctx* ctx) {
+    PK_BIND(ctx);
     if (!ctx) return PK_ERR_INVALID_ARG;
     PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PK_OK;
@@ -136,6 +137,7 @@ int pk_ctx_sync(pk_ctx* ctx) {
 
 // ---- buffers -----------------------------------------------------------------------------------
 int pk_buf_alloc(pk_ctx* ctx, size_t n, pk_buf** out) {
+    PK_BIND(ctx);
     if (!ctx || !out) return PK_ERR_INVALID_ARG;
     *out = nullptr;
     pk_buf* b = new pk_buf();
@@ -149,6 +151,7 @@ int pk_buf_alloc(pk_ctx* ctx, size_t n, pk_buf** out) {
     return PK_OK;
 }
 void pk_buf_free(pk_ctx* ctx, pk_buf* b) {
+    PK_BIND(ctx);
     if (!b) return;
     if (ctx && ctx->stream)
         cudaFreeAsync(b->d, ctx->stream);  // stream-ordered: no host synchronisation
@@ -159,24 +162,28 @@ void pk_buf_free(pk_ctx* ctx, pk_buf* b) {
 size_t pk_buf_len(const pk_buf* b) { return b ? b->n : 0; }
 void* pk_buf_device_ptr(pk_buf* b) { return b ? b->d : nullptr; }
 int pk_buf_upload(pk_ctx* ctx, pk_buf* dst, size_t off, const uint64_t* host, size_t n) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, dst && host && off + n <= dst->n, "pk_buf_upload: range out of bounds");
     PK_CUDA(ctx, cudaMemcpyAsync((char*)dst->d + off * 32, host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PK_OK;
 }
 int pk_buf_download(pk_ctx* ctx, const pk_buf* src, size_t off, uint64_t* host, size_t n) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, src && host && off + n <= src->n, "pk_buf_download: range out of bounds");
     PK_CUDA(ctx, cudaMemcpyAsync(host, (const char*)src->d + off * 32, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
     PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PK_OK;
 }
 int pk_buf_copy(pk_ctx* ctx, pk_buf* dst, size_t doff, const pk_buf* src, size_t soff, size_t n) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, dst && src && doff + n <= dst->n && soff + n <= src->n, "pk_buf_copy: range out of bounds");
     PK_CUDA(ctx, cudaMemcpyAsync((char*)dst->d + doff * 32, (const char*)src->d + soff * 32, n * 32, cudaMemcpyDeviceToDevice,
                                  ctx->stream));
     return PK_OK;
 }
 int pk_buf_zero(pk_ctx* ctx, pk_buf* dst, size_t off, size_t n) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, dst && off + n <= dst->n, "pk_buf_zero: range out of bounds");
     PK_CUDA(ctx, cudaMemsetAsync((char*)dst->d + off * 32, 0, n * 32, ctx->stream));
     return PK_OK;
@@ -184,6 +191,7 @@ int pk_buf_zero(pk_ctx* ctx, pk_buf* dst, size_t off, size_t n) {
 
 // ---- Skyscraper ----------------------------------------------------------------------------------
 int pk_skyscraper_compress_many(pk_ctx* ctx, const uint8_t* messages, uint8_t* hashes, size_t n) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, ctx && (n == 0 || (messages && hashes)), "compress_many: null buffer");
     if (n == 0) return PK_OK;
     // bounded device staging so arbitrarily large host batches stream through
@@ -202,6 +210,7 @@ int pk_skyscraper_compress_many(pk_ctx* ctx, const uint8_t* messages, uint8_t* h
     return PK_OK;
 }
 int pk_skyscraper_compress_many_dev(pk_ctx* ctx, const pk_buf* messages, pk_buf* hashes, size_t n) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, messages && hashes && messages->n >= 2 * n && hashes->n >= n, "compress_many_dev: buffer too small");
     ctx->launches += launch_compress_many(ctx->stream, messages->d, hashes->d, n);
     PK_CUDA(ctx, cudaGetLastError());
@@ -233,6 +242,7 @@ static void f64_to_u256(double f, uint64_t out[4]) {
     }
 }
 int pk_pow_solve(pk_ctx* ctx, const uint64_t challenge[4], double bits, uint64_t* nonce) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, ctx && challenge && nonce, "pow_solve: null argument");
     // provekit/common/src/skyscraper/pow.rs:16: assert!((0.0..60.0).contains(&bits))
     PK_CHECK(ctx, bits >= 0.0 && bits < 60.0, "bits must be smaller than 60");
@@ -276,8 +286,10 @@ static int wavelet(pk_ctx* ctx, pk_buf* buf, int log_n, bool inverse) {
     PK_CUDA(ctx, cudaGetLastError());
     return PK_OK;
 }
-int pk_evals_to_coeffs(pk_ctx* ctx, pk_buf* buf, int log_n) { return wavelet(ctx, buf, log_n, true); }
-int pk_coeffs_to_evals(pk_ctx* ctx, pk_buf* buf, int log_n) { return wavelet(ctx, buf, log_n, false); }
+int pk_evals_to_coeffs(pk_ctx* ctx, pk_buf* buf, int log_n) {
+    PK_BIND(ctx); return wavelet(ctx, buf, log_n, true); }
+int pk_coeffs_to_evals(pk_ctx* ctx, pk_buf* buf, int log_n) {
+    PK_BIND(ctx); return wavelet(ctx, buf, log_n, false); }
 
 // ---- commit ------------------------------------------------------------------------------------
 static int rs_encode_raw(pk_ctx* ctx, const void* coeffs, int log_n, int log_inv_rate, int fold, void* leaves,
@@ -297,12 +309,14 @@ static int rs_encode_raw(pk_ctx* ctx, const void* coeffs, int log_n, int log_inv
 }
 int pk_rs_encode(pk_ctx* ctx, const pk_buf* coeffs, int log_n, int log_inv_rate, int fold, pk_buf* leaves,
                  size_t leaf_stride, size_t col_offset) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, coeffs && leaves && log_n >= 0 && log_n < 40 && coeffs->n >= ((size_t)1 << log_n), "rs_encode: coeffs too small");
     size_t rows = (size_t)1 << (log_n + log_inv_rate - fold);
     PK_CHECK(ctx, col_offset + ((size_t)1 << fold) <= leaf_stride && leaves->n >= rows * leaf_stride, "rs_encode: leaves too small");
     return rs_encode_raw(ctx, coeffs->d, log_n, log_inv_rate, fold, leaves->d, leaf_stride, col_offset);
 }
 int pk_merkle_build(pk_ctx* ctx, const pk_buf* leaves, size_t L, size_t w, pk_buf* nodes) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, leaves && nodes, "merkle_build: null buffer");
     if (w == 0) return set_err(ctx, PK_ERR_EMPTY_INPUT, "IncorrectInputLength(0)");
     PK_CHECK(ctx, L >= 2 && (L & (L - 1)) == 0, "merkle_build: leaf count must be a power of two >= 2");
@@ -320,6 +334,7 @@ int pk_merkle_build(pk_ctx* ctx, const pk_buf* leaves, size_t L, size_t w, pk_bu
 }
 int pk_commit_batch(pk_ctx* ctx, const pk_buf* const* coeffs, int batch, int log_n, int log_inv_rate, int fold,
                     pk_commitment** out, uint64_t root_out[4]) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, ctx && coeffs && out && root_out && batch >= 1, "commit_batch: bad arguments");
     PK_CHECK(ctx, fold == 4 && log_n >= fold && log_n + log_inv_rate - fold >= 1, "commit_batch: bad sizes");
     for (int b = 0; b < batch; b++) PK_CHECK(ctx, coeffs[b] && coeffs[b]->n >= ((size_t)1 << log_n), "commit_batch: poly %d too small", b);
@@ -360,6 +375,7 @@ int pk_commit_batch(pk_ctx* ctx, const pk_buf* const* coeffs, int batch, int log
     return PK_OK;
 }
 void pk_commit_free(pk_ctx* ctx, pk_commitment* c) {
+    PK_BIND(ctx);
     if (!c) return;
     if (ctx && ctx->stream) {
         if (c->leaves) cudaFreeAsync(c->leaves, ctx->stream);
@@ -376,6 +392,7 @@ size_t pk_commit_leaf_width(const pk_commitment* c) { return c ? c->w : 0; }
 int pk_commit_open(pk_ctx* ctx, const pk_commitment* c, const uint64_t* sorted_idx, size_t n_idx, uint64_t* leaves_out,
                    uint64_t* sibling_out, uint64_t* prefix_len_out, uint64_t* suffix_out, uint64_t* suffix_len_out,
                    size_t suffix_cap) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, ctx && c && (n_idx == 0 || (sorted_idx && leaves_out && sibling_out && prefix_len_out && suffix_out && suffix_len_out)),
              "commit_open: null argument");
     if (n_idx == 0) return PK_OK;
@@ -435,6 +452,7 @@ static int build_point_tables(pk_ctx* ctx, const uint64_t* point, int nv, bool e
     return PK_OK;
 }
 int pk_eval_univariate_batch(pk_ctx* ctx, const pk_buf* const* coeffs, int k, size_t n, const uint64_t z[4], uint64_t* out) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, coeffs && z && out && k >= 1 && k <= 3 && n >= 1 && (n & (n - 1)) == 0, "eval_univariate: bad arguments");
     const void* ptrs[3] = {nullptr, nullptr, nullptr};
     for (int j = 0; j < k; j++) {
@@ -458,20 +476,24 @@ int pk_eval_univariate_batch(pk_ctx* ctx, const pk_buf* const* coeffs, int k, si
     return fetch_result(ctx, out, k);  // also orders the pageable `pt` upload before we return
 }
 int pk_eval_univariate(pk_ctx* ctx, const pk_buf* coeffs, size_t n, const uint64_t z[4], uint64_t out[4]) {
+    PK_BIND(ctx);
     return pk_eval_univariate_batch(ctx, &coeffs, 1, n, z, out);
 }
 int pk_axpy(pk_ctx* ctx, pk_buf* y, const pk_buf* x, const uint64_t a[4], size_t n) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, y && x && a && y->n >= n && x->n >= n, "axpy: buffer too small");
     ctx->launches += launch_axpy(ctx->stream, y->d, x->d, to_arg(a), n);
     PK_CUDA(ctx, cudaGetLastError());
     return PK_OK;
 }
 int pk_dot(pk_ctx* ctx, const pk_buf* a, const pk_buf* b, size_t n, uint64_t out[4]) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, a && b && out && a->n >= n && b->n >= n && n >= 1, "dot: buffer too small");
     ctx->launches += launch_dot(ctx->stream, a->d, b->d, n, ctx->d_partials, ctx->d_result);
     return fetch_result(ctx, out, 1);
 }
 int pk_multi_dot(pk_ctx* ctx, const pk_buf* const* a, int na, const pk_buf* const* b, int nb, size_t n, uint64_t* out) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, a && b && out && n >= 1 && ((na == 3 && nb == 2) || (na == 1 && nb == 2)), "multi_dot: unsupported shape");
     const void *pa[3] = {nullptr, nullptr, nullptr}, *pb[2] = {nullptr, nullptr};
     for (int i = 0; i < na; i++) {
@@ -486,6 +508,7 @@ int pk_multi_dot(pk_ctx* ctx, const pk_buf* const* a, int na, const pk_buf* cons
     return fetch_result(ctx, out, na * nb);
 }
 int pk_eval_eq_batch(pk_ctx* ctx, const uint64_t* points, size_t k, int n, const uint64_t* scalars, pk_buf* out) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, points && scalars && out && n >= 0 && n < 40 && out->n >= ((size_t)1 << n), "eval_eq: bad arguments");
     if (k == 0) return PK_OK;
     int lo = split_bits(n), hi = n - lo;
@@ -506,9 +529,11 @@ int pk_eval_eq_batch(pk_ctx* ctx, const uint64_t* points, size_t k, int n, const
     return PK_OK;
 }
 int pk_eval_eq(pk_ctx* ctx, const uint64_t* point, int n, const uint64_t scalar[4], pk_buf* out) {
+    PK_BIND(ctx);
     return pk_eval_eq_batch(ctx, point, 1, n, scalar, out);
 }
 int pk_mle_eval_batch(pk_ctx* ctx, const pk_buf* const* evals, int k, int log_n, const uint64_t* point, uint64_t* out) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, evals && point && out && k >= 1 && k <= 3 && log_n >= 0 && log_n < 40, "mle_eval: bad arguments");
     const void* ptrs[3] = {nullptr, nullptr, nullptr};
     for (int j = 0; j < k; j++) {
@@ -522,9 +547,11 @@ int pk_mle_eval_batch(pk_ctx* ctx, const pk_buf* const* evals, int k, int log_n,
     return fetch_result(ctx, out, k);
 }
 int pk_mle_eval(pk_ctx* ctx, const pk_buf* evals, int log_n, const uint64_t* point, uint64_t out[4]) {
+    PK_BIND(ctx);
     return pk_mle_eval_batch(ctx, &evals, 1, log_n, point, out);
 }
 int pk_fold_coeffs(pk_ctx* ctx, const pk_buf* coeffs, int log_n, const uint64_t* r, int k, pk_buf* out) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, coeffs && r && out && k >= 0 && k <= 4 && log_n >= k && log_n < 40, "fold_coeffs: bad arguments");
     PK_CHECK(ctx, coeffs->n >= ((size_t)1 << log_n) && out->n >= ((size_t)1 << (log_n - k)), "fold_coeffs: buffer too small");
     PK_TRY(ensure_small(ctx, 4 * 32));
@@ -538,6 +565,7 @@ int pk_fold_coeffs(pk_ctx* ctx, const pk_buf* coeffs, int log_n, const uint64_t*
 // ---- sumchecks -----------------------------------------------------------------------------------
 int pk_zk_sumcheck_round(pk_ctx* ctx, pk_buf* a, pk_buf* b, pk_buf* c, pk_buf* eq, int log_n, const uint64_t* fold,
                          uint64_t out3[12]) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, a && b && c && eq && out3, "zk_sumcheck_round: null argument");
     // sumcheck.rs:21-24: power of two, >= 2, equal lengths; :27: >= 4 when folding
     PK_CHECK(ctx, log_n >= (fold ? 2 : 1) && log_n < 40, "zk_sumcheck_round: size must be >= %d", fold ? 4 : 2);
@@ -554,6 +582,7 @@ int pk_zk_sumcheck_round(pk_ctx* ctx, pk_buf* a, pk_buf* b, pk_buf* c, pk_buf* e
 }
 int pk_whir_sumcheck_round(pk_ctx* ctx, const pk_buf* p_in, const pk_buf* w_in, pk_buf* p_out, pk_buf* w_out, int log_n,
                            const uint64_t* fold, uint64_t out3[12]) {
+    PK_BIND(ctx);
     PK_CHECK(ctx, p_in && w_in && out3, "whir_sumcheck_round: null argument");
     PK_CHECK(ctx, log_n >= (fold ? 2 : 1) && log_n < 40, "whir_sumcheck_round: size must be >= %d", fold ? 4 : 2);
     size_t n = (size_t)1 << log_n;
@@ -574,6 +603,7 @@ int pk_whir_sumcheck_round(pk_ctx* ctx, const pk_buf* p_in, const pk_buf* w_in, 
 
 // ---- per-kernel-class device timing (CUDA events on the ctx stream) --------------------------------
 int pk_profile_begin(pk_ctx* ctx) {
+    PK_BIND(ctx);
     if (!ctx) return PK_ERR_INVALID_ARG;
     PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->profiling = true;
@@ -582,6 +612,7 @@ int pk_profile_begin(pk_ctx* ctx) {
     return PK_OK;
 }
 int pk_profile_end(pk_ctx* ctx, double ms_by_class[8], uint64_t launches_by_class[8], double max_ms_by_class[8]) {
+    PK_BIND(ctx);
     if (!ctx || !ms_by_class || !launches_by_class || !max_ms_by_class) return PK_ERR_INVALID_ARG;
     PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 8; i++) {
@@ -605,9 +636,11 @@ int pk_profile_end(pk_ctx* ctx, double ms_by_class[8], uint64_t launches_by_clas
 // ---- measurement helper (not part of the reference surface) ----------------------------------------
 static int modmul_bench(pk_ctx* ctx, size_t n_threads, int iters, float* ms_out, bool square);
 int pk_modmul_bench(pk_ctx* ctx, size_t n_threads, int iters, float* ms_out) {
+    PK_BIND(ctx);
     return modmul_bench(ctx, n_threads, iters, ms_out, false);
 }
 int pk_modsqr_bench(pk_ctx* ctx, size_t n_threads, int iters, float* ms_out) {
+    PK_BIND(ctx);
     return modmul_bench(ctx, n_threads, iters, ms_out, true);
 }
 static int modmul_bench(pk_ctx* ctx, size_t n_threads, int iters, float* ms_out, bool square) {
