@@ -96,6 +96,22 @@ int pk_rs_encode(pk_ctx *ctx, const pk_buf *coeffs, int log_n, int log_inv_rate,
 /* nodes: 2L elements, heap order (nodes[1] = root, leaf digests at [L,2L)), canonical digests */
 int pk_merkle_build(pk_ctx *ctx, const pk_buf *leaves, size_t num_leaves, size_t leaf_width, pk_buf *nodes);
 
+/* ---- multi-GPU commit (one process per GPU): the codeword's columns are sharded across ranks for the
+ * NTT, its rows (Merkle leaves) across ranks for hashing.  The exchange between the two layouts is FUSED into the last
+ * NTT pass: every rank stores its columns of row r straight into the leaf block of the rank that owns r, through
+ * CUDA-IPC mapped peer memory (NVLink P2P stores) — no staging buffer, no separate all-to-all kernel.  Sub-tree roots are
+ * then all-gathered by the caller (NCCL, 32 B per rank) and combined with pk_merkle_combine_roots.
+ *   pk_buf_alloc_shared : a leaf block other processes can map;  pk_ipc_export/open/close : 64-byte cudaIpcMemHandle_t
+ *   pk_rs_encode_sharded: columns [col_first, col_first+n_cols) of one polynomial -> peer_leaves[row / (rows/n_peers)] */
+int pk_buf_alloc_shared(pk_ctx *ctx, size_t n_elems, pk_buf **out);
+int pk_ipc_export(pk_ctx *ctx, const pk_buf *buf, uint8_t handle_out[64]);
+int pk_ipc_open(pk_ctx *ctx, const uint8_t handle[64], void **dptr_out);
+int pk_ipc_close(pk_ctx *ctx, void *dptr);
+int pk_rs_encode_sharded(pk_ctx *ctx, const pk_buf *coeffs, int log_n, int log_inv_rate, int fold, int col_first,
+                         int n_cols, void *const *peer_leaves, int n_peers, size_t leaf_stride, size_t col_offset);
+/* n canonical sub-tree roots (rank order, n a power of two <= 8) -> canonical root of the whole tree */
+int pk_merkle_combine_roots(pk_ctx *ctx, const uint64_t *roots, int n, uint64_t root_out[4]);
+
 /* ---- seam: MerkleTree::generate_multi_proof + STIR answers [whir/ark-crypto-primitives] -------
  * sorted_idx: strictly increasing leaf indexes.  leaves_out: n_idx * leaf_width elements (Montgomery).
  * ark MultiPath pieces (canonical 32-byte digests): sibling_out[n_idx*4]; prefix_len_out[n_idx];

@@ -76,6 +76,12 @@ def lib() -> ctypes.CDLL:
         "pk_commit_leaf_width": (sz, [vp]),
         "pk_rs_encode": (c_int, [vp, vp, c_int, c_int, c_int, vp, sz, sz]),
         "pk_merkle_build": (c_int, [vp, vp, sz, sz, vp]),
+        "pk_buf_alloc_shared": (c_int, [vp, sz, POINTER(vp)]),
+        "pk_ipc_export": (c_int, [vp, vp, vp]),
+        "pk_ipc_open": (c_int, [vp, vp, POINTER(vp)]),
+        "pk_ipc_close": (c_int, [vp, vp]),
+        "pk_rs_encode_sharded": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, POINTER(vp), c_int, sz, sz]),
+        "pk_merkle_combine_roots": (c_int, [vp, u64p, c_int, u64p]),
         "pk_commit_open": (c_int, [vp, vp, u64p, sz, u64p, u64p, u64p, u64p, u64p, sz]),
         "pk_eval_univariate": (c_int, [vp, vp, sz, u64p, u64p]),
         "pk_eval_univariate_batch": (c_int, [vp, POINTER(vp), c_int, sz, u64p, u64p]),

@@ -127,6 +127,42 @@ class Context:
     def buffer(self, n: int) -> Buffer:
         return Buffer(self, n)
 
+    def buffer_shared(self, n: int) -> Buffer:
+        """IPC-exportable buffer (cudaMalloc) for the leaf block of a sharded commit."""
+        b = Buffer.__new__(Buffer)
+        b.ctx, b.n = self, n
+        h = c_void_p()
+        self._chk(self.L.pk_buf_alloc_shared(self.h, n, byref(h)))
+        b.h = h
+        return b
+
+    def ipc_export(self, buf: Buffer) -> bytes:
+        out = (ctypes.c_uint8 * 64)()
+        self._chk(self.L.pk_ipc_export(self.h, buf.h, out))
+        return bytes(out)
+
+    def ipc_open(self, handle: bytes) -> int:
+        h = (ctypes.c_uint8 * 64)(*handle)
+        p = c_void_p()
+        self._chk(self.L.pk_ipc_open(self.h, h, byref(p)))
+        return p.value
+
+    def ipc_close(self, dptr: int):
+        self._chk(self.L.pk_ipc_close(self.h, c_void_p(dptr)))
+
+    def rs_encode_sharded(self, coeffs: Buffer, log_n: int, log_inv_rate: int, col_first: int, n_cols: int, peer_ptrs,
+                          leaf_stride: int, col_offset: int, fold: int = 4):
+        """columns [col_first, col_first+n_cols) of one polynomial; row r -> peer_ptrs[r // (rows/len(peer_ptrs))]"""
+        arr = (c_void_p * len(peer_ptrs))(*[c_void_p(p) for p in peer_ptrs])
+        self._chk(self.L.pk_rs_encode_sharded(self.h, coeffs.h, log_n, log_inv_rate, fold, col_first, n_cols, arr,
+                                              len(peer_ptrs), leaf_stride, col_offset))
+
+    def merkle_combine_roots(self, roots) -> np.ndarray:
+        r = np.ascontiguousarray(roots, dtype=np.uint64).reshape(-1, 4)
+        out = np.empty(4, np.uint64)
+        self._chk(self.L.pk_merkle_combine_roots(self.h, _p(r), len(r), _p(out)))
+        return out
+
     def upload(self, arr) -> Buffer:
         arr = _fe(arr)
         return Buffer(self, len(arr)).upload(arr)

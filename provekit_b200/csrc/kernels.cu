@@ -259,22 +259,31 @@ int launch_twiddle_table(cudaStream_t st, void* table, int log_m, const uint32_t
 // K1 Reed-Solomon encode: 16 column NTTs ("prover helps" layout), E coset NTTs of size N' per column,
 // multi-pass radix-2 DIF in shared-memory tiles of 2^S points x 16 columns.
 // ------------------------------------------------------------------------------------------------
-constexpr int NTT_TILE_BITS = 7;  // 2^7 points x 16 columns x 32 B = 64 KB
+constexpr int NTT_TILE_ELEMS_LOG = 11;  // at most 2^11 elements x 32 B = 64 KB per tile (2^7 points x 16 columns, 2^9 x 4, ...)
+constexpr int NTT_MAX_PEERS = 8;
 struct NttPass {
     const fr* in;
-    fr* out;
+    fr* out;           // scratch (non-last pass)
     const fr* W;       // twiddle table, order 2^tbl_log
     int tbl_shift;     // omega_M^e = W[e << tbl_shift]
     int L, l, S, logE, logM;
     int first, last;
+    int nc_log;        // this launch handles 2^nc_log of the polynomial's 16 columns, starting at col0
+    int col0;
+    // last pass: row r of the codeword goes to peer[r >> rows_per_peer_log] (this GPU's own block or a peer GPU's
+    // block mapped through CUDA IPC) at local row r & mask: the all-to-all of the sharded commit is fused into the
+    // final NTT pass as NVLink peer stores
+    fr* peer[NTT_MAX_PEERS];
+    int rows_per_peer_log;
     size_t leaf_stride, col_offset;
 };
 __global__ void __launch_bounds__(256) k_ntt_pass(NttPass P) {
     extern __shared__ uint4 smem_raw[];
-    const int S = P.S, l = P.l, L = P.L;
-    SmTile sm(smem_raw, 16 << S);
+    const int S = P.S, l = P.l, L = P.L, ncl = P.nc_log;
+    const int NC = 1 << ncl;
+    SmTile sm(smem_raw, NC << S);
     // twiddles of this tile, staged once: stage hb (half size h = 2^hb) owns tw[h-1 .. 2h-2]
-    fr* tw = reinterpret_cast<fr*>(smem_raw + (32 << S));
+    fr* tw = reinterpret_cast<fr*>(smem_raw + (2 * NC << S));
     const uint32_t tile = blockIdx.x;
     const uint32_t s = tile >> (L - S);
     const uint32_t t = tile & ((1u << (L - S)) - 1u);
@@ -283,12 +292,12 @@ __global__ void __launch_bounds__(256) k_ntt_pass(NttPass P) {
     const uint32_t qbase = (H << (l + S)) | Lo;
     const int npts = 1 << S;
     const uint32_t halfM = 1u << (P.logM - 1);
-    for (int idx = threadIdx.x; idx < npts * 16; idx += blockDim.x) {
-        uint32_t mid = idx >> 4, k = idx & 15;
+    for (int idx = threadIdx.x; idx < npts * NC; idx += blockDim.x) {
+        uint32_t mid = idx >> ncl, k = idx & (NC - 1);
         uint32_t q = qbase | (mid << l);
         fr x;
         if (P.first) {
-            x = fr_load_nc(&P.in[(size_t)q * 16 + k]);
+            x = fr_load_nc(&P.in[(size_t)q * 16 + P.col0 + k]);
             if (s) {  // coset twist omega_M^(s*q)
                 uint32_t e = s * q;
                 bool neg = e >= halfM;
@@ -297,7 +306,7 @@ __global__ void __launch_bounds__(256) k_ntt_pass(NttPass P) {
                 if (neg) x = fr_neg(x);
             }
         } else {
-            x = fr_load(&P.in[(((size_t)s << L) + q) * 16 + k]);
+            x = fr_load(&P.in[((((size_t)s << L) + q) << ncl) + k]);
         }
         sm.put(idx, x);
     }
@@ -311,48 +320,55 @@ __global__ void __launch_bounds__(256) k_ntt_pass(NttPass P) {
     for (int hb = S - 1; hb >= 0; hb--) {
         const int h = 1 << hb;
         const bool unit_twiddle = (Lo == 0) && (hb == 0);  // the only stage whose twiddle is 1 for the whole tile
-        for (int bf = threadIdx.x; bf < (npts / 2) * 16; bf += blockDim.x) {
-            int k = bf & 15, b = bf >> 4;
+        for (int bf = threadIdx.x; bf < (npts / 2) * NC; bf += blockDim.x) {
+            int k = bf & (NC - 1), b = bf >> ncl;
             int j = b & (h - 1);
             int i0 = ((b >> hb) << (hb + 1)) | j;
             int i1 = i0 + h;
-            fr a = sm.get(i0 * 16 + k), bb = sm.get(i1 * 16 + k);
-            sm.put(i0 * 16 + k, fr_add(a, bb));
+            fr a = sm.get((i0 << ncl) + k), bb = sm.get((i1 << ncl) + k);
+            sm.put((i0 << ncl) + k, fr_add(a, bb));
             fr d = fr_sub(a, bb);
             if (!unit_twiddle && (j | Lo)) d = fr_mul(d, fr_load(&tw[h - 1 + j]));
-            sm.put(i1 * 16 + k, d);
+            sm.put((i1 << ncl) + k, d);
         }
         __syncthreads();
     }
-    for (int idx = threadIdx.x; idx < npts * 16; idx += blockDim.x) {
-        uint32_t mid = idx >> 4, k = idx & 15;
+    for (int idx = threadIdx.x; idx < npts * NC; idx += blockDim.x) {
+        uint32_t mid = idx >> ncl, k = idx & (NC - 1);
         uint32_t q = qbase | (mid << l);
         if (P.last) {
             uint32_t tq = L ? (__brev(q) >> (32 - L)) : 0u;
             size_t row = (size_t)s + ((size_t)tq << P.logE);
-            fr_store(&P.out[row * P.leaf_stride + P.col_offset + k], sm.get(idx));
+            fr* base = P.peer[row >> P.rows_per_peer_log];
+            size_t lrow = row & (((size_t)1 << P.rows_per_peer_log) - 1);
+            fr_store(&base[lrow * P.leaf_stride + P.col_offset + P.col0 + k], sm.get(idx));
         } else {
-            fr_store(&P.out[(((size_t)s << L) + q) * 16 + k], sm.get(idx));
+            fr_store(&P.out[((((size_t)s << L) + q) << ncl) + k], sm.get(idx));
         }
     }
 }
-int launch_rs_encode(cudaStream_t st, const void* coeffs, int log_n, int log_inv_rate, int fold, void* out,
-                     size_t leaf_stride, size_t col_offset, void* scratch, const void* table, int table_log_m) {
+// columns [col0, col0 + 2^nc_log) of one polynomial; peers: n_peers leaf blocks of (rows / n_peers) rows each
+int launch_rs_encode_cols(cudaStream_t st, const void* coeffs, int log_n, int log_inv_rate, int fold, int col0, int nc_log,
+                          void* const* peers, int n_peers, size_t leaf_stride, size_t col_offset, void* scratch,
+                          const void* table, int table_log_m) {
     // fold must be 4 (16 columns): FoldingFactor::Constant(4), provekit/r1cs-compiler/src/whir_r1cs.rs:44
     int L = log_n - fold;
     int logE = log_inv_rate;
     int logM = L + logE;
     int launches = 0;
     int done = 0;  // stage bits processed, from the top
-    int npass = L == 0 ? 1 : (L + NTT_TILE_BITS - 1) / NTT_TILE_BITS;
+    int tile_bits = NTT_TILE_ELEMS_LOG - nc_log;
+    int npass = L == 0 ? 1 : (L + tile_bits - 1) / tile_bits;
+    int peers_log = 0;
+    while ((1 << peers_log) < n_peers) peers_log++;
     for (int p = 0; p < npass; p++) {
         // balanced split (17 -> 6+6+5 rather than 7+7+3): tiny tiles waste the load/store phases
         int S = (L - done + (npass - p) - 1) / (npass - p);
-        NttPass P;
+        NttPass P = {};
         P.first = p == 0;
         P.last = p == npass - 1;
         P.in = (const fr*)(P.first ? coeffs : scratch);
-        P.out = (fr*)(P.last ? out : scratch);
+        P.out = (fr*)scratch;
         P.W = (const fr*)table;
         P.tbl_shift = table_log_m - logM;
         P.L = L;
@@ -360,15 +376,26 @@ int launch_rs_encode(cudaStream_t st, const void* coeffs, int log_n, int log_inv
         P.l = L - done - S;
         P.logE = logE;
         P.logM = logM < 1 ? 1 : logM;
+        P.nc_log = nc_log;
+        P.col0 = col0;
+        for (int i = 0; i < n_peers; i++) P.peer[i] = (fr*)peers[i];
+        P.rows_per_peer_log = logM - peers_log;
         P.leaf_stride = leaf_stride;
         P.col_offset = col_offset;
         unsigned grid = 1u << (logE + L - S);
-        size_t smem = ((size_t)32 * 16 << S) + ((size_t)32 << S);
-        k_ntt_pass<<<grid, S >= 5 ? 256 : (S >= 4 ? 128 : 32), smem, st>>>(P);
+        int elems_log = S + nc_log;
+        size_t smem = ((size_t)32 << elems_log) + ((size_t)32 << S);
+        k_ntt_pass<<<grid, elems_log >= 9 ? 256 : (elems_log >= 8 ? 128 : 32), smem, st>>>(P);
         launches++;
         done += S;
     }
     return launches;
+}
+int launch_rs_encode(cudaStream_t st, const void* coeffs, int log_n, int log_inv_rate, int fold, void* out,
+                     size_t leaf_stride, size_t col_offset, void* scratch, const void* table, int table_log_m) {
+    void* peers[1] = {out};
+    return launch_rs_encode_cols(st, coeffs, log_n, log_inv_rate, fold, 0, 4, peers, 1, leaf_stride, col_offset, scratch, table,
+                                 table_log_m);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -611,37 +638,41 @@ int launch_fold_coeffs(cudaStream_t st, const void* coeffs, int log_n, const voi
 // the map of provekit/prover/src/whir_r1cs.rs:284-291).  MSB pairing: i <-> i + len/2.
 // ------------------------------------------------------------------------------------------------
 template <bool FOLD>
-__global__ void __launch_bounds__(256) k_zk_sumcheck(fr* a, fr* b, fr* c, fr* eq, size_t half, fr_arg foldv, fr* partials,
+__global__ void __launch_bounds__(256, 2) k_zk_sumcheck(fr* a, fr* b, fr* c, fr* eq, size_t half, fr_arg foldv, fr* partials,
                                                      fr* result) {
     // `half` = (length after folding) / 2; before folding the arrays are 4*half long
     fr acc[3] = {fr_zero(), fr_zero(), fr_zero()};
     fr f = arg_fr(foldv);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
-        fr v0[4], v1[4];
-        fr* arr[4] = {a, b, c, eq};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (FOLD) {
-                fr x0 = fr_load(&arr[k][i]), x1 = fr_load(&arr[k][i + half]);
-                fr x2 = fr_load(&arr[k][i + 2 * half]), x3 = fr_load(&arr[k][i + 3 * half]);
-                v0[k] = fr_add(x0, fr_mul(f, fr_sub(x2, x0)));
-                v1[k] = fr_add(x1, fr_mul(f, fr_sub(x3, x1)));
-                fr_store(&arr[k][i], v0[k]);
-                fr_store(&arr[k][i + half], v1[k]);
-            } else {
-                v0[k] = fr_load(&arr[k][i]);
-                v1[k] = fr_load(&arr[k][i + half]);
-            }
+    // one array at a time, (x0, d = x1 - x0) per array, products formed as soon as their inputs exist: keeps the live set
+    // near 90 registers so two 256-thread blocks fit per SM
+    auto fetch = [&](fr* x, size_t i, fr& x0, fr& d) {
+        if (FOLD) {
+            fr q0 = fr_load(&x[i]), q2 = fr_load(&x[i + 2 * half]);
+            x0 = fr_add(q0, fr_mul(f, fr_sub(q2, q0)));
+            fr_store(&x[i], x0);
+            fr q1 = fr_load(&x[i + half]), q3 = fr_load(&x[i + 3 * half]);
+            fr x1 = fr_add(q1, fr_mul(f, fr_sub(q3, q1)));
+            fr_store(&x[i + half], x1);
+            d = fr_sub(x1, x0);
+        } else {
+            x0 = fr_load(&x[i]);
+            d = fr_sub(fr_load(&x[i + half]), x0);
         }
-        const fr &a0 = v0[0], &a1 = v1[0], &b0 = v0[1], &b1 = v1[1], &c0 = v0[2], &c1 = v1[2], &e0 = v0[3], &e1 = v1[3];
-        fr f0 = fr_mul(e0, fr_sub(fr_mul(a0, b0), c0));
-        fr am = fr_sub(fr_dbl(a0), a1), bm = fr_sub(fr_dbl(b0), b1);
-        fr cm = fr_sub(fr_dbl(c0), c1), em = fr_sub(fr_dbl(e0), e1);
-        fr fm = fr_mul(em, fr_sub(fr_mul(am, bm), cm));
-        fr fi = fr_mul(fr_mul(fr_sub(e1, e0), fr_sub(a1, a0)), fr_sub(b1, b0));
-        acc[0] = fr_add(acc[0], f0);
-        acc[1] = fr_add(acc[1], fm);
-        acc[2] = fr_add(acc[2], fi);
+    };
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+        fr x0, d, y0, e;
+        fetch(a, i, x0, d);
+        fetch(b, i, y0, e);
+        fr t1 = fr_mul(x0, y0);                          // a0 b0
+        fr t2 = fr_mul(fr_sub(x0, d), fr_sub(y0, e));    // (2a0 - a1)(2b0 - b1)
+        fr t3 = fr_mul(d, e);                            // (a1 - a0)(b1 - b0)
+        fetch(c, i, x0, d);
+        t1 = fr_sub(t1, x0);                             // a0 b0 - c0
+        t2 = fr_sub(t2, fr_sub(x0, d));                  // ... - (2c0 - c1)
+        fetch(eq, i, x0, d);
+        acc[0] = fr_add(acc[0], fr_mul(x0, t1));                 // f(0)
+        acc[1] = fr_add(acc[1], fr_mul(fr_sub(x0, d), t2));      // f(-1)
+        acc[2] = fr_add(acc[2], fr_mul(d, t3));                  // f(inf)
     }
     grid_reduce<3>(acc, partials, result);
 }
@@ -661,7 +692,7 @@ int launch_zk_sumcheck_round(cudaStream_t st, void* a, void* b, void* c, void* e
 // K7 WHIR sumcheck round [whir SumcheckSingle]: LSB pairing (2i, 2i+1), sends h(0), h(1), h(2).
 // ------------------------------------------------------------------------------------------------
 template <bool FOLD>
-__global__ void __launch_bounds__(256) k_whir_sumcheck(const fr* __restrict__ p_in, const fr* __restrict__ w_in,
+__global__ void __launch_bounds__(256, 2) k_whir_sumcheck(const fr* __restrict__ p_in, const fr* __restrict__ w_in,
                                                        fr* p_out, fr* w_out, size_t pairs, fr_arg foldv, fr* partials,
                                                        fr* result) {
     fr acc[3] = {fr_zero(), fr_zero(), fr_zero()};

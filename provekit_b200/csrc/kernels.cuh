@@ -30,6 +30,12 @@ int launch_twiddle_table(cudaStream_t st, void* table, int log_m, const uint32_t
 int launch_rs_encode(cudaStream_t st, const void* coeffs, int log_n, int log_inv_rate, int fold, void* out,
                      size_t leaf_stride, size_t col_offset, void* scratch, const void* table, int table_log_m);
 
+// sharded variant: only columns [col0, col0 + 2^nc_log) of the polynomial; row r of the codeword is stored into
+// peers[r / (rows / n_peers)] (device pointers of this or of peer GPUs) at its local row index
+int launch_rs_encode_cols(cudaStream_t st, const void* coeffs, int log_n, int log_inv_rate, int fold, int col0, int nc_log,
+                          void* const* peers, int n_peers, size_t leaf_stride, size_t col_offset, void* scratch,
+                          const void* table, int table_log_m);
+
 // K2 Merkle: leaves Montgomery, nodes canonical heap order
 int launch_merkle_leaves(cudaStream_t st, const void* leaves, size_t L, size_t w, void* nodes);
 int launch_merkle_upper(cudaStream_t st, size_t L, void* nodes);

@@ -43,6 +43,7 @@ struct pk_ctx {
 struct pk_buf {
     void* d = nullptr;
     size_t n = 0;
+    bool plain = false;  // cudaMalloc'd (IPC-exportable) instead of stream-ordered pool memory
 };
 
 struct pk_commitment {

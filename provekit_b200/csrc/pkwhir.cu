@@ -153,6 +153,12 @@ int pk_buf_alloc(pk_ctx* ctx, size_t n, pk_buf** out) {
 void pk_buf_free(pk_ctx* ctx, pk_buf* b) {
     PK_BIND(ctx);
     if (!b) return;
+    if (b->plain) {
+        if (ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
+        cudaFree(b->d);
+        delete b;
+        return;
+    }
     if (ctx && ctx->stream)
         cudaFreeAsync(b->d, ctx->stream);  // stream-ordered: no host synchronisation
     else
@@ -186,6 +192,46 @@ int pk_buf_zero(pk_ctx* ctx, pk_buf* dst, size_t off, size_t n) {
     PK_BIND(ctx);
     PK_CHECK(ctx, dst && off + n <= dst->n, "pk_buf_zero: range out of bounds");
     PK_CUDA(ctx, cudaMemsetAsync((char*)dst->d + off * 32, 0, n * 32, ctx->stream));
+    return PK_OK;
+}
+
+// ---- multi-GPU plumbing: IPC-exportable buffers --------------------------------------------------
+int pk_buf_alloc_shared(pk_ctx* ctx, size_t n, pk_buf** out) {
+    PK_BIND(ctx);
+    if (!ctx || !out) return PK_ERR_INVALID_ARG;
+    *out = nullptr;
+    pk_buf* b = new pk_buf();
+    b->n = n;
+    b->plain = true;  // cudaMalloc (not the stream-ordered pool): legacy CUDA IPC can export it
+    cudaError_t e = cudaMalloc(&b->d, n ? n * 32 : 32);
+    if (e != cudaSuccess) {
+        delete b;
+        return set_err(ctx, PK_ERR_OOM, "cudaMalloc(%zu elems): %s", n, cudaGetErrorString(e));
+    }
+    *out = b;
+    return PK_OK;
+}
+int pk_ipc_export(pk_ctx* ctx, const pk_buf* buf, uint8_t handle_out[64]) {
+    PK_BIND(ctx);
+    PK_CHECK(ctx, ctx && buf && handle_out && buf->plain, "ipc_export: needs a buffer from pk_buf_alloc_shared");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    PK_CUDA(ctx, cudaIpcGetMemHandle(&h, buf->d));
+    std::memcpy(handle_out, &h, 64);
+    return PK_OK;
+}
+int pk_ipc_open(pk_ctx* ctx, const uint8_t handle[64], void** dptr_out) {
+    PK_BIND(ctx);
+    PK_CHECK(ctx, ctx && handle && dptr_out, "ipc_open: null argument");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    PK_CUDA(ctx, cudaIpcOpenMemHandle(dptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return PK_OK;
+}
+int pk_ipc_close(pk_ctx* ctx, void* dptr) {
+    PK_BIND(ctx);
+    PK_CHECK(ctx, ctx && dptr, "ipc_close: null argument");
+    PK_CUDA(ctx, cudaIpcCloseMemHandle(dptr));
     return PK_OK;
 }
 
@@ -314,6 +360,44 @@ int pk_rs_encode(pk_ctx* ctx, const pk_buf* coeffs, int log_n, int log_inv_rate,
     size_t rows = (size_t)1 << (log_n + log_inv_rate - fold);
     PK_CHECK(ctx, col_offset + ((size_t)1 << fold) <= leaf_stride && leaves->n >= rows * leaf_stride, "rs_encode: leaves too small");
     return rs_encode_raw(ctx, coeffs->d, log_n, log_inv_rate, fold, leaves->d, leaf_stride, col_offset);
+}
+int pk_rs_encode_sharded(pk_ctx* ctx, const pk_buf* coeffs, int log_n, int log_inv_rate, int fold, int col_first, int n_cols,
+                         void* const* peer_leaves, int n_peers, size_t leaf_stride, size_t col_offset) {
+    PK_BIND(ctx);
+    PK_CHECK(ctx, coeffs && peer_leaves && fold == 4, "rs_encode_sharded: bad arguments");
+    PK_CHECK(ctx, log_n >= fold && log_inv_rate >= 0 && log_n + log_inv_rate <= 28 && coeffs->n >= ((size_t)1 << log_n),
+             "rs_encode_sharded: bad sizes");
+    int nc_log = 0;
+    while ((1 << nc_log) < n_cols) nc_log++;
+    PK_CHECK(ctx, (1 << nc_log) == n_cols && n_cols >= 1 && n_cols <= 16 && col_first % n_cols == 0 && col_first + n_cols <= 16,
+             "rs_encode_sharded: columns must be an aligned power-of-two block of the 16");
+    int logM = log_n - fold + log_inv_rate;
+    PK_CHECK(ctx, n_peers >= 1 && n_peers <= 8 && (n_peers & (n_peers - 1)) == 0 && (1 << logM) >= n_peers,
+             "rs_encode_sharded: peers must be a power of two <= 8");
+    for (int i = 0; i < n_peers; i++) PK_CHECK(ctx, peer_leaves[i], "rs_encode_sharded: null peer pointer");
+    PK_CHECK(ctx, col_offset + 16 <= leaf_stride, "rs_encode_sharded: leaf_stride too small");
+    PK_TRY(ensure_twiddles(ctx, logM));
+    PK_TRY(ensure_scratch(ctx, ((size_t)n_cols << logM)));
+    {
+        ProfScope ps(ctx, PROF_NTT);
+        ctx->launches += launch_rs_encode_cols(ctx->stream, coeffs->d, log_n, log_inv_rate, fold, col_first, nc_log, peer_leaves,
+                                               n_peers, leaf_stride, col_offset, ctx->d_scratch, ctx->d_twiddles, ctx->twiddle_log_m);
+    }
+    PK_CUDA(ctx, cudaGetLastError());
+    return PK_OK;
+}
+// top of a sharded tree: `n` canonical sub-tree roots (n = power of two <= 8, rank order) -> canonical root
+int pk_merkle_combine_roots(pk_ctx* ctx, const uint64_t* roots, int n, uint64_t root_out[4]) {
+    PK_BIND(ctx);
+    PK_CHECK(ctx, ctx && roots && root_out && n >= 1 && n <= 8 && (n & (n - 1)) == 0, "combine_roots: bad arguments");
+    uint64_t cur[8 * 4], nxt[4 * 4];
+    std::memcpy(cur, roots, (size_t)n * 32);
+    for (int m = n; m > 1; m >>= 1) {
+        PK_TRY(pk_skyscraper_compress_many(ctx, (const uint8_t*)cur, (uint8_t*)nxt, (size_t)m / 2));
+        std::memcpy(cur, nxt, (size_t)(m / 2) * 32);
+    }
+    std::memcpy(root_out, cur, 32);
+    return PK_OK;
 }
 int pk_merkle_build(pk_ctx* ctx, const pk_buf* leaves, size_t L, size_t w, pk_buf* nodes) {
     PK_BIND(ctx);

@@ -341,3 +341,45 @@ def test_reductions_repeatable(ctx, orc):
         assert np.array_equal(ctx.dot(da, db, n), exp)
     da.free()
     db.free()
+
+
+@pytest.mark.parametrize("log_n,rate,n_cols,n_peers", [(12, 1, 16, 1), (12, 1, 8, 2), (14, 1, 4, 4), (13, 4, 4, 8), (16, 1, 8, 4),
+                                                       (18, 1, 4, 8), (8, 1, 16, 2)])
+def test_rs_encode_sharded_layout(ctx, orc, log_n, rate, n_cols, n_peers):
+    """Sharded commit building block on ONE GPU: column subsets + row blocks into separate 'peer' buffers must
+    reassemble to exactly the single-GPU codeword (the multi-process version only swaps local pointers for IPC ones)."""
+    a = rng_fr(4242 + log_n, 1 << log_n)
+    rows = 1 << (log_n + rate - 4)
+    w = 32  # batched layout: this polynomial occupies columns 16..31
+    exp = np.zeros((rows * w, 4), np.uint64)
+    orc.orc_rs_encode(ptr(a), log_n, rate, 4, ptr(exp), sz(w), sz(16))
+    coeffs = ctx.upload(a)
+    per = rows // n_peers
+    blocks = [ctx.buffer_shared(per * w).zero() for _ in range(n_peers)]
+    ptrs = [b.device_ptr for b in blocks]
+    for c0 in range(0, 16, n_cols):
+        ctx.rs_encode_sharded(coeffs, log_n, rate, c0, n_cols, ptrs, w, 16)
+    got = np.concatenate([b.download() for b in blocks])
+    assert np.array_equal(got, exp)
+    for b in blocks:
+        b.free()
+    coeffs.free()
+
+
+def test_merkle_combine_roots(ctx, orc):
+    L, w, G = 1 << 10, 16, 4
+    a = rng_fr(77, L * w)
+    nodes = np.zeros((2 * L, 4), np.uint64)
+    orc.orc_merkle_build(ptr(a), sz(L), sz(w), ptr(nodes), 2)
+    canon = np.zeros_like(nodes)
+    orc.orc_from_montgomery(ptr(nodes), ptr(canon), sz(2 * L))
+    sub = canon[G:2 * G]          # heap order: level with G nodes = the G sub-tree roots, left to right
+    assert np.array_equal(ctx.merkle_combine_roots(sub), canon[1])
+    # and each sub-tree root equals a local tree over that rank's rows
+    per = L // G
+    for r in range(G):
+        leaves, nd = ctx.upload(a[r * per * w:(r + 1) * per * w]), ctx.buffer(2 * per)
+        ctx.merkle_build(leaves, per, w, nd)
+        assert np.array_equal(nd.download(1, 1)[0], sub[r])
+        leaves.free()
+        nd.free()
