@@ -901,7 +901,7 @@ cudaError_t init_kernel_attributes() {
     if ((e = cudaFuncSetAttribute(k_wavelet_flat<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
     if ((e = cudaFuncSetAttribute(k_wavelet_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
     if ((e = cudaFuncSetAttribute(k_wavelet_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
-    if ((e = cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, smem + 4096))) return e;
+    if ((e = cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, smem + 32768))) return e;
     return cudaSuccess;
 }
 

@@ -29,7 +29,9 @@ def first_diff(a: bytes, b: bytes):
     return n if len(a) != len(b) else -1
 
 
-@pytest.mark.parametrize("nc,nfree", [(17, 5), (64, 40), (100, 300), (1000, 900), (5000, 3000), (1 << 15, 30000)])
+# sizes cover m mod 4 = 0..3 (final_sumcheck_rounds 0..3), 0..3 WHIR rounds, and a 2^17-coefficient witness polynomial
+@pytest.mark.parametrize("nc,nfree", [(9, 4), (17, 5), (20, 30), (64, 40), (100, 300), (300, 400), (1000, 900), (5000, 3000),
+                                      (5000, 9000), (1 << 15, 30000)])
 def test_gpu_proof_is_byte_identical_to_oracle(ctx, orc, nc, nfree):
     import provekit_b200 as pk
     r = SyntheticR1CS(nc, nfree, seed=nc)

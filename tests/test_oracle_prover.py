@@ -8,7 +8,8 @@ from oracle import pyref as o
 from r1cs_util import SyntheticR1CS, oracle_prove, oracle_verify
 
 
-@pytest.mark.parametrize("nc,nfree", [(64, 40), (100, 300), (1000, 900), (17, 5)])
+# (nc, nfree) chosen so that m = ceil(log2(nc + nfree)) + 1 covers every residue mod 4 (final_sumcheck_rounds 0..3)
+@pytest.mark.parametrize("nc,nfree", [(64, 40), (100, 300), (1000, 900), (17, 5), (20, 30), (300, 400), (9, 4)])
 def test_prove_verify_roundtrip(orc, nc, nfree):
     r = SyntheticR1CS(nc, nfree, seed=nc)
     proof = oracle_prove(orc, r)
