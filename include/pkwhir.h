@@ -201,6 +201,12 @@ void pk_free(void *p);
  * [7] everything else, [8] total */
 void pk_prover_timings(const pk_prover *p, double out[9]);
 
+/* ---- `.np` proof container (provekit/common/src/file/bin.rs:16-60, file/mod.rs:33-37): 20-byte header
+ * (magic, "NPSProof", version 0.0) + zstd(postcard(NoirProof{WhirR1CSProof{transcript}})).  No device needed.
+ * Outputs are malloc'd (pk_free).  decode accepts what `noir-r1cs prove` writes; encode writes what `verify` reads. */
+int pk_np_encode(const uint8_t *transcript, size_t len, uint8_t **file_out, size_t *file_len);
+int pk_np_decode(const uint8_t *file, size_t len, uint8_t **transcript_out, size_t *transcript_len);
+
 /* ---- measurement: CUDA-event timing per kernel class on the ctx stream (no reference counterpart).
  * Between begin and end every launch group is bracketed by an event pair.  Classes: 0 RS-encode NTT
  * passes, 1 Merkle leaf hashing, 2 Merkle upper levels, 3 zk-sumcheck rounds, 4 WHIR sumcheck rounds,

@@ -100,6 +100,8 @@ def lib() -> ctypes.CDLL:
         "pk_prove": (c_int, [vp, u64p, POINTER(Rand), POINTER(vp), POINTER(sz)]),
         "pk_free": (None, [vp]),
         "pk_prover_timings": (None, [vp, POINTER(c_double)]),
+        "pk_np_encode": (c_int, [vp, sz, POINTER(vp), POINTER(sz)]),
+        "pk_np_decode": (c_int, [vp, sz, POINTER(vp), POINTER(sz)]),
         "pk_profile_begin": (c_int, [vp]),
         "pk_profile_end": (c_int, [vp, POINTER(c_double), POINTER(c_uint64), POINTER(c_double)]),
         "pk_prover_upload_inputs": (c_int, [vp, u64p, POINTER(Rand)]),

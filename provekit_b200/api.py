@@ -271,6 +271,32 @@ class Context:
         return ms.value
 
 
+def np_encode(transcript: bytes) -> bytes:
+    """WhirR1CSProof transcript -> bytes of a `.np` file (provekit/common/src/file/bin.rs write_bin)."""
+    L = _abi.lib()
+    src = np.frombuffer(transcript, dtype=np.uint8)
+    out, n = c_void_p(), c_size_t()
+    rc = L.pk_np_encode(_p(src) if len(src) else None, len(src), byref(out), byref(n))
+    if rc != 0:
+        raise PkError(rc, "pk_np_encode failed")
+    data = ctypes.string_at(out, n.value)
+    L.pk_free(out)
+    return data
+
+
+def np_decode(file_bytes: bytes) -> bytes:
+    """bytes of a `.np` file -> transcript (read_bin + postcard)."""
+    L = _abi.lib()
+    src = np.frombuffer(file_bytes, dtype=np.uint8)
+    out, n = c_void_p(), c_size_t()
+    rc = L.pk_np_decode(_p(src), len(src), byref(out), byref(n))
+    if rc != 0:
+        raise PkError(rc, "pk_np_decode: not a valid .np container")
+    data = ctypes.string_at(out, n.value)
+    L.pk_free(out)
+    return data
+
+
 class Prover:
     """WhirR1CSProver::prove (provekit/prover/src/whir_r1cs.rs:42-100) over a device-resident R1CS.
     `r1cs` is a dict with num_constraints, num_witnesses, interned (k,4) and a/b/c = (row_start u64,

@@ -74,17 +74,6 @@ static __device__ __forceinline__ void block_reduce(fr (&acc)[NS], fr* out) {
     }
 }
 
-template <int NS>
-__global__ void __launch_bounds__(256) k_reduce_partials(const fr* __restrict__ partials, int nblocks, fr* result) {
-    fr acc[NS];
-#pragma unroll
-    for (int s = 0; s < NS; s++) acc[s] = fr_zero();
-    for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
-#pragma unroll
-        for (int s = 0; s < NS; s++) acc[s] = fr_add(acc[s], fr_load(&partials[b * NS + s]));
-    block_reduce<NS>(acc, result);
-}
-
 static __device__ __forceinline__ fr fr_load_cg(const void* p) {  // L2 (cache-global) load: sees other blocks' stores
     const uint4* q = reinterpret_cast<const uint4*>(p);
     uint4 a = __ldcg(q), b = __ldcg(q + 1);

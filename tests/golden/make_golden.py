@@ -64,6 +64,10 @@ def main():
     out = os.path.join(HERE, "poseidon-1000.transcript.bin")
     open(out, "wb").write(transcript)
     print("wrote", out, len(transcript), hashlib.sha256(transcript).hexdigest())
+    # the container itself, verbatim (258 KB): exercises pk_np_decode on bytes the reference wrote
+    out2 = os.path.join(HERE, "poseidon-1000.np")
+    open(out2, "wb").write(raw)
+    print("wrote", out2, len(raw), hashlib.sha256(raw).hexdigest())
 
 
 if __name__ == "__main__":
