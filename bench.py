@@ -49,35 +49,39 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  ONE sampler per job
+    (rank 0) covering the GPUs in use, at 0.5 s period: nvidia-smi takes a driver-wide lock, so a sampler per rank
+    stalls CUDA calls of every process on an 8-GPU box."""
 
-    def __init__(self, index=0):
+    def __init__(self, n_gpus=1):
         super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        self.n_gpus, self.rows, self._halt = n_gpus, [], threading.Event()
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+        q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self._halt.is_set():
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([x.strip() for x in o.split(",")])
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=10).stdout.strip()
+                for ln in o.splitlines():
+                    r = [x.strip() for x in ln.split(",")]
+                    if len(r) >= 7 and r[0].isdigit() and int(r[0]) < self.n_gpus:
+                        self.rows.append(r[1:])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.5)
 
     def finish(self):
         self._halt.set()
-        self.join(timeout=6)
+        self.join(timeout=12)
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "sm_min_mhz": sm[0] if sm else None, "reasons": reasons, "samples": len(self.rows)}
 
 
 def oracle_structs(r1cs, rnd):
@@ -251,9 +255,10 @@ def main():
     for p_ in provers:
         p_.upload_inputs(witness, rnd_p)
         p_.prove_staged()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(world) if rank == 0 else None
     barrier()
-    sampler.start()
+    if sampler:
+        sampler.start()
     # (a) one proof at a time with per-kernel CUDA events: kernel durations for the roofline
     launches0 = ctx.launches
     ctx._chk(ctx.L.pk_profile_begin(ctx.h))
@@ -273,6 +278,8 @@ def main():
     # (b) the measured configuration: n_fl proofs in flight
     barrier()
     if n_fl > 1:
+        run_concurrent(lambda p_: p_.prove_staged(), n_fl)  # thread start-up / first concurrent launches, untimed
+        barrier()
         dev_ms, dev_wall, _ = run_concurrent(lambda p_: p_.prove_staged(), args.steps)
     else:
         dev_ms = single_ms
@@ -281,11 +288,12 @@ def main():
     single_ms = max_over_ranks(single_ms)
 
     # ---- e2e arm: host buffers in, transcript out, every step ----
+    run_concurrent(lambda p_: p_.prove(witness, rnd_p), n_fl)
     barrier()
     e2e_ms, e2e_wall, proof = run_concurrent(lambda p_: p_.prove(witness, rnd_p), args.steps)
     barrier()
     e2e_ms = max_over_ranks(max(e2e_ms, e2e_wall))
-    clocks = sampler.finish()
+    clocks = sampler.finish() if sampler else None
 
     if rank == 0:
         peak, peak_src = measured_peak()
