@@ -7,8 +7,10 @@ Skyscraper Merkle tree), zk-sumcheck, blinding WHIR, R1CS weights, witness WHIR 
 PoW grinding, STIR openings) with the Fiat-Shamir transcript on the host.
 
   value  proofs/s with the proof's inputs (witness, masks) already resident in HBM  (pk_prove_staged)
-  e2e    proofs/s through the C-ABI call with HOST (pinned) buffers: H2D of witness+masks and D2H of the
-         transcript inside the timed region                                          (pk_prove)
+  e2e    proofs/s through the C-ABI call with HOST (pinned) buffers: H2D of the witness (+ a 32-byte seed; the
+         masks the reference draws from thread_rng inside prove are drawn on the device, pk_rng_fill) and D2H of
+         the transcript inside the timed region                                      (pk_prove_seeded)
+         e2e_host_masks: the same with the masks supplied as host arrays (pk_prove, 128 MB H2D per proof)
   roofline  dominant kernel (Merkle leaf hashing): algorithmic bytes of its launches in one proof divided by
             their CUDA-event time, against the measured HBM peak (MEASURED_PEAKS.json)
   cpu_baseline  the CPU oracle (C restatement of the reference algorithms, OpenMP on all host cores) timed on
@@ -124,7 +126,8 @@ def base_line(args, workload, r1cs):
         "metric": "noir-r1cs prove proofs/sec (WHIR hot path: RS-encode NTT + Skyscraper Merkle + sumcheck/fold)",
         "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (256-bit BN254-Fr Montgomery)",
-        "data": "synthetic satisfiable R1CS with the shapes of the reference fixture poseidon-1000.nps; seeded masks",
+        "data": "synthetic satisfiable R1CS with the shapes of the reference fixture poseidon-1000.nps; masks from a "
+                "32-byte seed (ChaCha12 counter stream, the reference's thread_rng construction)",
         "config": {"workload": f"{workload}: {r1cs['num_constraints']} constraints x {r1cs['num_witnesses']} witnesses, "
                                f"m={m}, m_0={m0}, blinding m={mh}, WHIR fold 4, rate 1/2, batch 2, 128-bit ConjectureList",
                    "parallelism": f"proof-level replicas x{args.gpus} (one process per GPU, no data-path collective)",
@@ -167,7 +170,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="poseidon-1000", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--in-flight", type=int, default=2,
+    ap.add_argument("--in-flight", type=int, default=4,
                     help="independent proofs in flight per GPU (own ctx/stream/host thread each): the host<->device "
                          "round trips of one proof (~120 challenges) are hidden behind the kernels of the other")
     args = ap.parse_args()
@@ -212,12 +215,14 @@ def main():
     provers = [pk.Prover(c, r1cs) for c in ctxs]
     streams = [torch.cuda.ExternalStream(c.stream) for c in ctxs]
     ctx, prover, stream = ctxs[0], provers[0], streams[0]
-    h2d = 32 * (r1cs["num_witnesses"] + sum(len(v) for v in rnd.values()))
+    h2d = 32 * r1cs["num_witnesses"] + 32
+    h2d_host_masks = 32 * (r1cs["num_witnesses"] + sum(len(v) for v in rnd.values()))
+    seed = bytes((17 * i + 3 + rank) & 0xFF for i in range(32))
 
     proof = None
     for _ in range(args.warmup):
         for p_ in provers:
-            proof = p_.prove(witness, rnd_p)
+            proof = p_.prove_seeded(witness, seed)
     d2h = len(proof) + 32 * (3 * (m0 + 4 * 12) + 64)  # transcript + per-round result scalars (approx.)
 
     def run_concurrent(fn, steps):
@@ -253,7 +258,7 @@ def main():
 
     # ---- device-resident arm: inputs staged once per worker, K proofs from HBM ----
     for p_ in provers:
-        p_.upload_inputs(witness, rnd_p)
+        p_.upload_inputs_seeded(witness, seed)
         p_.prove_staged()
     sampler = ClockSampler(world) if rank == 0 else None
     barrier()
@@ -288,11 +293,17 @@ def main():
     single_ms = max_over_ranks(single_ms)
 
     # ---- e2e arm: host buffers in, transcript out, every step ----
-    run_concurrent(lambda p_: p_.prove(witness, rnd_p), n_fl)
+    run_concurrent(lambda p_: p_.prove_seeded(witness, seed), n_fl)
     barrier()
-    e2e_ms, e2e_wall, proof = run_concurrent(lambda p_: p_.prove(witness, rnd_p), args.steps)
+    e2e_ms, e2e_wall, proof = run_concurrent(lambda p_: p_.prove_seeded(witness, seed), args.steps)
     barrier()
     e2e_ms = max_over_ranks(max(e2e_ms, e2e_wall))
+    # the same with the masks as host arrays (the explicit-mask entry point the parity tests use)
+    run_concurrent(lambda p_: p_.prove(witness, rnd_p), n_fl)
+    barrier()
+    hm_ms, hm_wall, _ = run_concurrent(lambda p_: p_.prove(witness, rnd_p), args.steps)
+    barrier()
+    hm_ms = max_over_ranks(max(hm_ms, hm_wall))
     clocks = sampler.finish() if sampler else None
 
     if rank == 0:
@@ -303,7 +314,9 @@ def main():
         line.update({"value": value, "ms_per_step": dev_ms / args.steps, "ms_per_step_one_in_flight": single_ms / args.steps,
                      "gpu_launches": int(launches), "clocks": clocks,
                      "e2e": {"value": aggregate_throughput(args.steps, world, e2e_ms), "unit": "proofs/s", "h2d_bytes_per_step": int(h2d),
-                             "d2h_bytes_per_step": int(d2h)}})
+                             "d2h_bytes_per_step": int(d2h)},
+                     "e2e_host_masks": {"value": aggregate_throughput(args.steps, world, hm_ms), "unit": "proofs/s",
+                                        "h2d_bytes_per_step": int(h2d_host_masks), "d2h_bytes_per_step": int(d2h)}})
         # roofline of the dominant kernel: Merkle leaf hashing of the witness commitment (L = 2^(m-3) leaves of 32)
         L = 1 << (m + 1 - 4)
         leaf_bytes = 32 * (L * 32 + L)           # read L*w elements, write L digests (leaf level of K2)
@@ -336,7 +349,11 @@ def main():
             import oracle
             oracle.build()
             orc = oracle.lib()
-            cs, rs = oracle_structs(r1cs, rnd)
+            # the CPU twin of the device mask generator gives the oracle the same masks the GPU proof used
+            masks = {k: np.zeros((n, 4), np.uint64) for k, n in
+                     (("mask_w", 1 << (m - 1)), ("g_w", 1 << m), ("blind", 4 * m0), ("mask_h", 1 << (mh - 1)), ("g_h", 1 << mh))}
+            orc.orc_rng_masks(seed, m, m0, mh, *[a.ctypes.data_as(ctypes.c_void_p) for a in masks.values()])
+            cs, rs = oracle_structs(r1cs, masks)
             dt, cpu_proof = cpu_prove_once(orc, cs, rs, r1cs["witness"])
             line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "proofs/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "1 full proof of the same workload (same witness, masks); C restatement of the "

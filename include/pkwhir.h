@@ -195,6 +195,15 @@ int pk_prove(pk_prover *p, const uint64_t *witness, const pk_rand *rnd, uint8_t 
  * H2D staging of witness + masks, then the proof itself from the staged inputs (repeatable). */
 int pk_prover_upload_inputs(pk_prover *p, const uint64_t *witness, const pk_rand *rnd);
 int pk_prove_staged(pk_prover *p, uint8_t **out, size_t *out_len);
+/* Masks drawn on the device: the reference draws them inside prove from thread_rng (a ChaCha12 stream; Fp::rand
+ * rejection-samples 254-bit strings; provekit/common/src/utils/zk_utils.rs:13-22, provekit/prover/src/whir_r1cs.rs:211-225).
+ * pk_rng_fill writes n uniform field elements: element i = first candidate < p among the 256-bit halves (top word
+ * masked to 30 bits) of ChaCha12 blocks keyed by `seed` with state words 12..15 = (i lo, i hi, stream, attempt).
+ * pk_prove_seeded = pk_prove with streams 0..4 of `seed` as mask_w, g_w, blind, mask_h, g_h: only the witness is
+ * copied host->device.  The caller supplies 32 fresh bytes of OS entropy per proof. */
+int pk_rng_fill(pk_ctx *ctx, pk_buf *dst, size_t off, size_t n, const uint8_t seed[32], uint32_t stream);
+int pk_prover_upload_inputs_seeded(pk_prover *p, const uint64_t *witness, const uint8_t seed[32]);
+int pk_prove_seeded(pk_prover *p, const uint64_t *witness, const uint8_t seed[32], uint8_t **out, size_t *out_len);
 void pk_free(void *p);
 /* host wall-clock seconds per stage of the last pk_prove: [0] witness commit (NTT+Merkle), [1] H2D staging of the inputs,
  * [2] zk-sumcheck, [3] WHIR sumcheck rounds, [4] PoW, [5] STIR openings, [6] R1CS mat-vec + weights,

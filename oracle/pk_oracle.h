@@ -59,6 +59,12 @@ void orc_zk_sumcheck_round(uint64_t *a, uint64_t *b, uint64_t *c, uint64_t *eq, 
 void orc_whir_sumcheck_round(uint64_t *p, uint64_t *w, int log_n, const uint64_t *fold,
                              uint64_t out3[12]);
 
+/* ---- mask generator (oracle/rng.c): ChaCha12 counter stream -> uniform Fr, the CPU twin of pk_rng_fill ---- */
+void orc_chacha_block(const uint32_t in[16], int rounds, uint32_t out[16]);
+void orc_rng_fill(uint64_t *out, size_t n, const uint8_t seed[32], uint32_t stream);
+void orc_rng_masks(const uint8_t seed[32], int m, int m0, int mh, uint64_t *mask_w, uint64_t *g_w, uint64_t *blind,
+                   uint64_t *mask_h, uint64_t *g_h);
+
 /* ---- full prover / verifier (oracle/prover.c) ---- */
 typedef struct {
     uint64_t num_rows, num_cols, nnz;

@@ -448,3 +448,41 @@ def whir_config(num_variables: int, batch_size: int = 2, security_level: int = 1
                 final_pow_bits=float(max(0, security_level - fq * log_inv_rate)),
                 final_log_inv_rate=log_inv_rate, final_sumcheck_rounds=final_sumcheck_rounds,
                 final_folding_pow_bits=0.0, final_domain_log=domain_log, batch_size=batch_size)
+
+
+# ---------------------------------------------------------------------------------------------
+# Mask generator (twin of pk_rng_fill / oracle/rng.c): ChaCha12 counter stream -> uniform Fr.
+# The reference draws masks with F::rand(&mut thread_rng()) (provekit/common/src/utils/zk_utils.rs:13-22):
+# a ChaCha12 stream, rejection sampling of 254-bit strings below p.  Block function = RFC 8439 section 2.3.
+# ---------------------------------------------------------------------------------------------
+def chacha_block(state: list[int], rounds: int) -> list[int]:
+    x = list(state)
+
+    def qr(a, b, c, d):
+        x[a] = (x[a] + x[b]) & 0xFFFFFFFF; x[d] ^= x[a]; x[d] = ((x[d] << 16) | (x[d] >> 16)) & 0xFFFFFFFF
+        x[c] = (x[c] + x[d]) & 0xFFFFFFFF; x[b] ^= x[c]; x[b] = ((x[b] << 12) | (x[b] >> 20)) & 0xFFFFFFFF
+        x[a] = (x[a] + x[b]) & 0xFFFFFFFF; x[d] ^= x[a]; x[d] = ((x[d] << 8) | (x[d] >> 24)) & 0xFFFFFFFF
+        x[c] = (x[c] + x[d]) & 0xFFFFFFFF; x[b] ^= x[c]; x[b] = ((x[b] << 7) | (x[b] >> 25)) & 0xFFFFFFFF
+
+    for _ in range(rounds // 2):
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
+    return [(a + b) & 0xFFFFFFFF for a, b in zip(x, state)]
+
+
+CHACHA_CONST = [0x61707865, 0x3320646E, 0x79622D32, 0x6B206574]
+
+
+def rng_element(seed: bytes, stream: int, i: int) -> int:
+    """Element i of stream `stream`: the integer whose 32 LE bytes are the element's in-memory (Montgomery) form."""
+    key = [int.from_bytes(seed[4 * k:4 * k + 4], "little") for k in range(8)]
+    attempt = 0
+    while True:
+        blk = chacha_block(CHACHA_CONST + key + [i & 0xFFFFFFFF, i >> 32, stream, attempt], 12)
+        for c in range(2):
+            w = blk[8 * c:8 * c + 8]
+            w[7] &= 0x3FFFFFFF
+            v = sum(x << (32 * k) for k, x in enumerate(w))
+            if v < P:
+                return v
+        attempt += 1

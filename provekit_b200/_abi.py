@@ -106,6 +106,9 @@ def lib() -> ctypes.CDLL:
         "pk_profile_end": (c_int, [vp, POINTER(c_double), POINTER(c_uint64), POINTER(c_double)]),
         "pk_prover_upload_inputs": (c_int, [vp, u64p, POINTER(Rand)]),
         "pk_prove_staged": (c_int, [vp, POINTER(vp), POINTER(sz)]),
+        "pk_rng_fill": (c_int, [vp, vp, sz, sz, c_char_p, c_uint32]),
+        "pk_prover_upload_inputs_seeded": (c_int, [vp, u64p, c_char_p]),
+        "pk_prove_seeded": (c_int, [vp, u64p, c_char_p, POINTER(vp), POINTER(sz)]),
         "pk_modmul_bench": (c_int, [vp, sz, c_int, POINTER(c_float)]),
         "pk_modsqr_bench": (c_int, [vp, sz, c_int, POINTER(c_float)]),
     }

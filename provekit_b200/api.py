@@ -51,6 +51,12 @@ class Buffer:
         self.ctx._chk(self.ctx.L.pk_buf_zero(self.ctx.h, self.h, off, self.n - off if n is None else n))
         return self
 
+    def rng_fill(self, seed: bytes, stream: int, off=0, n=None):
+        """n uniform field elements from the ChaCha12 counter stream (seed, stream) — pk_rng_fill."""
+        assert len(seed) == 32
+        self.ctx._chk(self.ctx.L.pk_rng_fill(self.ctx.h, self.h, off, self.n - off if n is None else n, seed, stream))
+        return self
+
     def free(self):
         if self.h:
             self.ctx.L.pk_buf_free(self.ctx.h, self.h)
@@ -342,6 +348,19 @@ class Prover:
         w = _fe(witness)
         rs, _keep = self._rand(rand)
         self.ctx._chk(self.ctx.L.pk_prover_upload_inputs(self.h, _p(w), byref(rs)))
+
+    def prove_seeded(self, witness, seed: bytes) -> bytes:
+        """pk_prove with the masks drawn on the device from a 32-byte seed: only the witness crosses PCIe."""
+        assert len(seed) == 32
+        w = _fe(witness)
+        out, n = c_void_p(), c_size_t()
+        self.ctx._chk(self.ctx.L.pk_prove_seeded(self.h, _p(w), seed, byref(out), byref(n)))
+        return self._take(out, n)
+
+    def upload_inputs_seeded(self, witness, seed: bytes):
+        assert len(seed) == 32
+        w = _fe(witness)
+        self.ctx._chk(self.ctx.L.pk_prover_upload_inputs_seeded(self.h, _p(w), seed))
 
     def prove_staged(self) -> bytes:
         out, n = c_void_p(), c_size_t()

@@ -771,6 +771,41 @@ int pk_prover_upload_inputs(pk_prover* p, const uint64_t* witness, const pk_rand
     p->staged = true;
     return PK_OK;
 }
+// same staging with the masks drawn ON THE DEVICE from `seed` (pk_rng_fill streams 0..4 = mask_w, g_w, blind, mask_h,
+// g_h): only the witness crosses PCIe.  The reference draws them from thread_rng inside prove (whir_r1cs.rs:211-225).
+int pk_prover_upload_inputs_seeded(pk_prover* p, const uint64_t* witness, const uint8_t seed[32]) {
+    if (!p) return PK_ERR_INVALID_ARG;
+    pk_ctx* ctx = p->ctx;
+    PK_BIND(ctx);
+    PK_CHECK(ctx, witness && seed, "upload_inputs_seeded: null argument");
+    const size_t half = (size_t)1 << (p->m - 1), N = (size_t)1 << p->m;
+    const size_t halfh = (size_t)1 << (p->mh - 1), Nh = (size_t)1 << p->mh;
+    const size_t nb = 4 * (size_t)p->m0;
+    if (!p->masked_w) {
+        PK_TRY(pk_buf_alloc(ctx, N, &p->masked_w));
+        PK_TRY(pk_buf_alloc(ctx, N, &p->g_w));
+        PK_TRY(pk_buf_alloc(ctx, Nh, &p->masked_h));
+        PK_TRY(pk_buf_alloc(ctx, Nh, &p->g_h));
+    }
+    double t0 = now_s();
+    cudaStream_t st = ctx->stream;
+    PK_CUDA(ctx, cudaMemcpyAsync(p->masked_w->d, witness, p->num_witnesses * 32, cudaMemcpyHostToDevice, st));
+    PK_CUDA(ctx, cudaMemsetAsync((char*)p->masked_w->d + p->num_witnesses * 32, 0, (half - p->num_witnesses) * 32, st));
+    PK_TRY(pk_rng_fill(ctx, p->masked_w, half, half, seed, 0));
+    PK_TRY(pk_rng_fill(ctx, p->g_w, 0, N, seed, 1));
+    PK_CUDA(ctx, cudaMemsetAsync(p->masked_h->d, 0, halfh * 32, st));
+    PK_TRY(pk_rng_fill(ctx, p->masked_h, 0, nb, seed, 2));
+    PK_TRY(pk_rng_fill(ctx, p->masked_h, halfh, halfh, seed, 3));
+    PK_TRY(pk_rng_fill(ctx, p->g_h, 0, Nh, seed, 4));
+    p->blind.resize(nb);
+    PK_CUDA(ctx, cudaMemcpyAsync(p->blind.data(), p->masked_h->d, nb * 32, cudaMemcpyDeviceToHost, st));
+    PK_CUDA(ctx, cudaStreamSynchronize(st));
+    std::memset(p->timings, 0, sizeof p->timings);
+    p->timings[1] = now_s() - t0;
+    p->timings[8] = p->timings[1];
+    p->staged = true;
+    return PK_OK;
+}
 int pk_prove_staged(pk_prover* p, uint8_t** out, size_t* out_len) {
     if (!p) return PK_ERR_INVALID_ARG;
     pk_ctx* ctx = p->ctx;
@@ -796,6 +831,10 @@ int pk_prove(pk_prover* p, const uint64_t* witness, const pk_rand* rnd, uint8_t*
     PK_TRY(pk_prover_upload_inputs(p, witness, rnd));
     int rc = pk_prove_staged(p, out, out_len);
     return rc;
+}
+int pk_prove_seeded(pk_prover* p, const uint64_t* witness, const uint8_t seed[32], uint8_t** out, size_t* out_len) {
+    PK_TRY(pk_prover_upload_inputs_seeded(p, witness, seed));
+    return pk_prove_staged(p, out, out_len);
 }
 void pk_free(void* p) { std::free(p); }
 void pk_prover_timings(const pk_prover* p, double out[9]) {

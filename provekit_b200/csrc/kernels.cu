@@ -883,6 +883,73 @@ int launch_modmul_bench(cudaStream_t st, void* data, size_t n_threads, int iters
     return 1;
 }
 
+// ------------------------------------------------------------------------------------------------
+// mask generator: the device twin of `F::rand(&mut thread_rng())` (provekit/common/src/utils/zk_utils.rs:13-22,
+// provekit/prover/src/whir_r1cs.rs:211-225).  thread_rng is a ChaCha12 stream and Fp::rand rejection-samples
+// 254-bit strings below p; here the stream is counter based, one thread per element:
+//   block(i, a) = ChaCha12(key, words 12..15 = (i lo, i hi, stream, a)); candidates block(i,0)[0..8),
+//   block(i,0)[8..16), block(i,1)[0..8), ... (top word masked to 30 bits); the first one < p becomes the element's
+//   in-memory (Montgomery) representation.  ALU-pipe only (add / xor / funnel shift); 64 B of stream per element.
+// ------------------------------------------------------------------------------------------------
+struct rng_key {
+    uint32_t k[8];
+};
+#define PK_QR(a, b, c, d)                                \
+    a += b; d ^= a; d = __funnelshift_l(d, d, 16);       \
+    c += d; b ^= c; b = __funnelshift_l(b, b, 12);       \
+    a += b; d ^= a; d = __funnelshift_l(d, d, 8);        \
+    c += d; b ^= c; b = __funnelshift_l(b, b, 7)
+__global__ void __launch_bounds__(256) k_rng_fill(fr* out, size_t n, rng_key key, uint32_t stream) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
+#pragma unroll
+    for (int k = 0; k < 8; k++) in[4 + k] = key.k[k];
+    in[12] = (uint32_t)i;
+    in[13] = (uint32_t)((uint64_t)i >> 32);
+    in[14] = stream;
+    for (uint32_t attempt = 0;; attempt++) {
+        in[15] = attempt;
+        uint32_t x[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = in[k];
+#pragma unroll 1
+        for (int r = 0; r < 12; r += 2) {
+            PK_QR(x[0], x[4], x[8], x[12]);
+            PK_QR(x[1], x[5], x[9], x[13]);
+            PK_QR(x[2], x[6], x[10], x[14]);
+            PK_QR(x[3], x[7], x[11], x[15]);
+            PK_QR(x[0], x[5], x[10], x[15]);
+            PK_QR(x[1], x[6], x[11], x[12]);
+            PK_QR(x[2], x[7], x[8], x[13]);
+            PK_QR(x[3], x[4], x[9], x[14]);
+        }
+        fr c0, c1, t;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            c0.v[k] = x[k] + in[k];
+            c1.v[k] = x[8 + k] + in[8 + k];
+        }
+        c0.v[7] &= 0x3fffffffu;
+        c1.v[7] &= 0x3fffffffu;
+        if (sub_p(t, c0)) {  // borrow: candidate < p
+            fr_store(&out[i], c0);
+            return;
+        }
+        if (sub_p(t, c1)) {
+            fr_store(&out[i], c1);
+            return;
+        }
+    }
+}
+int launch_rng_fill(cudaStream_t st, void* out, size_t n, const uint32_t key[8], uint32_t stream) {
+    if (n == 0) return 0;
+    rng_key K;
+    for (int i = 0; i < 8; i++) K.k[i] = key[i];
+    k_rng_fill<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((fr*)out, n, K, stream);
+    return 1;
+}
+
 cudaError_t init_kernel_attributes() {
     cudaError_t e;
     const int smem = 64 * 1024;

@@ -94,6 +94,9 @@ int launch_gather_paths(cudaStream_t st, const void* nodes, size_t L, const uint
 int launch_pow_scan(cudaStream_t st, fr_arg challenge, fr_arg threshold, uint64_t base, uint64_t count,
                     unsigned long long* best);
 
+// mask generator: n uniform field elements from the ChaCha12 counter stream (key, stream id); see kernels.cu
+int launch_rng_fill(cudaStream_t st, void* out, size_t n, const uint32_t key[8], uint32_t stream);
+
 // microbenchmark: chains `iters` dependent Montgomery multiplications per thread; returns launches
 int launch_modmul_bench(cudaStream_t st, void* data, size_t n_threads, int iters, bool square);
 

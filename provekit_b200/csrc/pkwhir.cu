@@ -195,6 +195,19 @@ int pk_buf_zero(pk_ctx* ctx, pk_buf* dst, size_t off, size_t n) {
     return PK_OK;
 }
 
+// ---- mask generator (device twin of F::rand(&mut thread_rng()), zk_utils.rs:13-22) ---------------------
+int pk_rng_fill(pk_ctx* ctx, pk_buf* dst, size_t off, size_t n, const uint8_t seed[32], uint32_t stream) {
+    PK_BIND(ctx);
+    PK_CHECK(ctx, dst && seed && off + n <= dst->n, "pk_rng_fill: range out of bounds");
+    uint32_t key[8];
+    for (int i = 0; i < 8; i++)
+        key[i] = (uint32_t)seed[4 * i] | ((uint32_t)seed[4 * i + 1] << 8) | ((uint32_t)seed[4 * i + 2] << 16) |
+                 ((uint32_t)seed[4 * i + 3] << 24);
+    ctx->launches += pk::launch_rng_fill(ctx->stream, (char*)dst->d + off * 32, n, key, stream);
+    PK_CUDA(ctx, cudaGetLastError());
+    return PK_OK;
+}
+
 // ---- multi-GPU plumbing: IPC-exportable buffers --------------------------------------------------
 int pk_buf_alloc_shared(pk_ctx* ctx, size_t n, pk_buf** out) {
     PK_BIND(ctx);
