@@ -6,7 +6,7 @@ import subprocess
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_size_t, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpkwhir.so")
+LIB_PATH = os.environ.get("PKWHIR_LIB") or os.path.join(_HERE, "libpkwhir.so")  # override: kernel-variant experiments
 _LIB = None
 
 
