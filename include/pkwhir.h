@@ -161,6 +161,25 @@ int pk_zk_sumcheck_round(pk_ctx *ctx, pk_buf *a, pk_buf *b, pk_buf *c, pk_buf *e
 int pk_whir_sumcheck_round(pk_ctx *ctx, const pk_buf *p_in, const pk_buf *w_in, pk_buf *p_out, pk_buf *w_out,
                            int log_n, const uint64_t *fold_or_null, uint64_t out3[12]);
 
+/* ---- multi-GPU sumchecks (one process per GPU) --------------------------------------
+ * The zk-sumcheck arrays are sharded by the LOW index bits (rank g owns x[(j << log2 G) | g]: the MSB pairs of
+ * sumcheck.rs:26-38 stay local), the WHIR arrays by the HIGH bits (contiguous blocks: the LSB pairs stay local).  A
+ * sharded round is the single-GPU kernel on the local shard followed by ONE one-warp kernel that stores the three
+ * partial sums into every peer's mailbox (CUDA-IPC mapped peer memory, NVLink P2P stores), waits for the peers'
+ * stores and adds them up: out3 is the GLOBAL round message on every rank, with no host-side collective.
+ *   mailbox: pk_buf_alloc_shared(ctx, pk_shard_mailbox_elems()), zeroed (pk_buf_zero) BEFORE any rank's first round
+ *   (barrier in the caller); mailboxes[r] = rank r's mailbox (own device pointer, or pk_ipc_open of the peer's handle).
+ * All ranks must call the sharded rounds in lock step; a peer that never arrives -> PK_ERR_CUDA after ~1 s, not a hang.
+ * When a shard is down to two elements the caller gathers the 2G survivors and finishes with the unsharded entry points
+ * (host logic: provekit_b200/sharded.py). */
+size_t pk_shard_mailbox_elems(void);
+int pk_shard_group_set(pk_ctx *ctx, int rank, int world, void *const *mailboxes);
+int pk_shard_group_clear(pk_ctx *ctx);
+int pk_zk_sumcheck_round_sharded(pk_ctx *ctx, pk_buf *a, pk_buf *b, pk_buf *c, pk_buf *eq, int log_n,
+                                 const uint64_t *fold_or_null, uint64_t out3[12]);
+int pk_whir_sumcheck_round_sharded(pk_ctx *ctx, const pk_buf *p_in, const pk_buf *w_in, pk_buf *p_out, pk_buf *w_out,
+                                   int log_n, const uint64_t *fold_or_null, uint64_t out3[12]);
+
 /* ---- seam: WhirR1CSProver::prove (provekit/prover/src/whir_r1cs.rs:42-100) --------------------
  * The whole hot path driven by this library's own host-side Fiat-Shamir transcript
  * (provekit_b200/csrc/host/).  R1CS in the reference's interned-CSR form

@@ -95,6 +95,11 @@ def lib() -> ctypes.CDLL:
         "pk_fold_coeffs": (c_int, [vp, vp, c_int, u64p, c_int, vp]),
         "pk_zk_sumcheck_round": (c_int, [vp, vp, vp, vp, vp, c_int, u64p, u64p]),
         "pk_whir_sumcheck_round": (c_int, [vp, vp, vp, vp, vp, c_int, u64p, u64p]),
+        "pk_shard_mailbox_elems": (sz, []),
+        "pk_shard_group_set": (c_int, [vp, c_int, c_int, POINTER(vp)]),
+        "pk_shard_group_clear": (c_int, [vp]),
+        "pk_zk_sumcheck_round_sharded": (c_int, [vp, vp, vp, vp, vp, c_int, u64p, u64p]),
+        "pk_whir_sumcheck_round_sharded": (c_int, [vp, vp, vp, vp, vp, c_int, u64p, u64p]),
         "pk_prover_create": (c_int, [vp, POINTER(R1CS), POINTER(vp)]),
         "pk_prover_destroy": (None, [vp]),
         "pk_prove": (c_int, [vp, u64p, POINTER(Rand), POINTER(vp), POINTER(sz)]),

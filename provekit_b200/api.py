@@ -47,6 +47,12 @@ class Buffer:
         self.ctx._chk(self.ctx.L.pk_buf_download(self.ctx.h, self.h, off, _p(out), n))
         return out
 
+    def clone(self) -> "Buffer":
+        """device-to-device copy into a fresh buffer (pk_buf_copy)"""
+        out = Buffer(self.ctx, self.n)
+        self.ctx._chk(self.ctx.L.pk_buf_copy(self.ctx.h, out.h, 0, self.h, 0, self.n))
+        return out
+
     def zero(self, off=0, n=None):
         self.ctx._chk(self.ctx.L.pk_buf_zero(self.ctx.h, self.h, off, self.n - off if n is None else n))
         return self
@@ -268,6 +274,33 @@ class Context:
         f = _fe(fold) if fold is not None else None
         self._chk(self.L.pk_whir_sumcheck_round(self.h, p_in.h, w_in.h, p_out.h if p_out else None,
                                                 w_out.h if w_out else None, log_n, _p(f), _p(out)))
+        return out
+
+    # ---- sharded sumchecks (one process per GPU; see include/pkwhir.h "multi-GPU sumchecks") ----
+    def shard_mailbox(self) -> Buffer:
+        """this rank's zeroed mailbox (IPC-exportable); barrier across ranks before the first sharded round"""
+        mb = self.buffer_shared(self.L.pk_shard_mailbox_elems())
+        mb.zero()
+        self.sync()
+        return mb
+
+    def shard_group(self, rank: int, world: int, mailbox_ptrs):
+        arr = (c_void_p * world)(*[c_void_p(int(p)) for p in mailbox_ptrs])
+        self._chk(self.L.pk_shard_group_set(self.h, rank, world, arr))
+
+    def sumcheck_fold_map_reduce_sharded(self, a: Buffer, b: Buffer, c: Buffer, eq: Buffer, log_n: int, fold=None) -> np.ndarray:
+        """the round on the local low-bit shard + exchange over peer memory: the GLOBAL [f(0), f(-1), f(inf)]"""
+        out = np.empty((3, 4), np.uint64)
+        f = _fe(fold) if fold is not None else None
+        self._chk(self.L.pk_zk_sumcheck_round_sharded(self.h, a.h, b.h, c.h, eq.h, log_n, _p(f), _p(out)))
+        return out
+
+    def whir_sumcheck_round_sharded(self, p_in: Buffer, w_in: Buffer, log_n: int, fold=None, p_out: Buffer = None,
+                                    w_out: Buffer = None) -> np.ndarray:
+        out = np.empty((3, 4), np.uint64)
+        f = _fe(fold) if fold is not None else None
+        self._chk(self.L.pk_whir_sumcheck_round_sharded(self.h, p_in.h, w_in.h, p_out.h if p_out else None,
+                                                        w_out.h if w_out else None, log_n, _p(f), _p(out)))
         return out
 
     def modmul_bench(self, n_threads: int, iters: int, square: bool = False) -> float:

@@ -726,6 +726,63 @@ int launch_whir_sumcheck_round(cudaStream_t st, const void* p_in, const void* w_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Sharded sumchecks: exchange of the round's partial sums over peer memory (see kernels.cuh)
+// ------------------------------------------------------------------------------------------------
+static __device__ __forceinline__ void st_sys(void* p, const fr& x) {  // peer-visible 128-bit stores
+    volatile uint4* q = reinterpret_cast<volatile uint4*>(p);
+    q[0].x = x.v[0]; q[0].y = x.v[1]; q[0].z = x.v[2]; q[0].w = x.v[3];
+    q[1].x = x.v[4]; q[1].y = x.v[5]; q[1].z = x.v[6]; q[1].w = x.v[7];
+}
+static __device__ __forceinline__ fr ld_sys(const void* p) {
+    const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(p);
+    fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = q[i];
+    return r;
+}
+__global__ void __launch_bounds__(32) k_shard_exchange(fr* result, ShardGroup G, uint32_t seq, uint32_t* status) {
+    const int lane = threadIdx.x;
+    const size_t slot = seq % SHARD_SLOTS;
+    bool ok = true;
+    fr v[3] = {fr_zero(), fr_zero(), fr_zero()};
+    if (lane < G.world) {
+        // publish my partial sums into cell [slot][my rank] of rank `lane` (my own mailbox included)
+        uint8_t* dst = G.mbox[lane] + (slot * SHARD_MAX_WORLD + G.rank) * SHARD_CELL_BYTES;
+#pragma unroll
+        for (int s = 0; s < 3; s++) st_sys(dst + 32 * s, fr_load(&result[s]));
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t*>(dst + 96) = seq;
+        // collect rank `lane`'s partial sums from my own mailbox
+        const uint8_t* src = G.mbox[G.rank] + (slot * SHARD_MAX_WORLD + lane) * SHARD_CELL_BYTES;
+        const volatile uint32_t* flag = reinterpret_cast<const volatile uint32_t*>(src + 96);
+        uint32_t spins = 0;
+        while (*flag != seq) {
+            if (++spins > (1u << 24)) {  // ~ a second: a peer never arrived; report instead of hanging the GPU
+                ok = false;
+                break;
+            }
+            __nanosleep(40);
+        }
+        __threadfence_system();
+        if (ok)
+#pragma unroll
+            for (int s = 0; s < 3; s++) v[s] = ld_sys(src + 32 * s);
+    }
+    ok = __all_sync(0xffffffffu, ok);
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) v[s] = fr_add(v[s], fr_shfl_down(v[s], d));
+        if (lane == 0) fr_store(&result[s], v[s]);
+    }
+    if (lane == 0) *status = ok ? 0u : 1u;
+}
+int launch_shard_exchange(cudaStream_t st, void* result, ShardGroup g, uint32_t seq, uint32_t* status) {
+    k_shard_exchange<<<1, 32, 0, st>>>((fr*)result, g, seq, status);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // R1CS sparse mat-vec (one thread per row; rows hold 1-3 entries in practice)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_spmv(const uint64_t* __restrict__ row_start, const uint32_t* __restrict__ col,

@@ -68,6 +68,20 @@ int launch_zk_sumcheck_round(cudaStream_t st, void* a, void* b, void* c, void* e
 int launch_whir_sumcheck_round(cudaStream_t st, const void* p_in, const void* w_in, void* p_out, void* w_out,
                                int log_n, bool has_fold, fr_arg fold, void* partials, void* result);
 
+// Sharded sumchecks: all-gather + field sum of the three partial sums of a round, fused behind the reduction as
+// NVLink peer stores.  Every rank owns a mailbox of SHARD_SLOTS x SHARD_MAX_WORLD cells of 128 B (96 B payload + sequence
+// flag) that its peers map through CUDA IPC; one warp publishes result[0..3) into cell [seq % SLOTS][rank] of every peer,
+// waits until its own cells carry `seq`, and replaces result[0..3) by the sum over ranks.  status: 0 ok, 1 timed out.
+constexpr int SHARD_MAX_WORLD = 8;
+constexpr int SHARD_SLOTS = 4;
+constexpr int SHARD_CELL_BYTES = 128;
+constexpr size_t SHARD_MAILBOX_BYTES = (size_t)SHARD_SLOTS * SHARD_MAX_WORLD * SHARD_CELL_BYTES;
+struct ShardGroup {
+    uint8_t* mbox[SHARD_MAX_WORLD];
+    int rank, world;
+};
+int launch_shard_exchange(cudaStream_t st, void* result, ShardGroup g, uint32_t seq, uint32_t* status);
+
 // interned-CSR sparse matrix x vector (provekit/common/src/sparse_matrix.rs:148-184): out[r] = sum_k
 // interned[val[k]] * x[col[k]] over row r.  The transposed product uses the same kernel on the CSC arrays.
 // Rows longer than SPMV_LONG_ROW are skipped by launch_spmv and handled by launch_spmv_long, which splits them

@@ -32,6 +32,10 @@ struct pk_ctx {
     size_t small_bytes = 0;
     void* h_stage = nullptr;      // pinned staging for uploads/downloads
     size_t h_stage_bytes = 0;
+    // sharded sumchecks (pk_shard_group_set): peer mailboxes and the lock-step sequence number of the exchange
+    pk::ShardGroup shard = {};
+    uint32_t shard_seq = 0;
+    uint32_t* d_shard_status = nullptr;
     // optional per-kernel-class CUDA-event timing (pk_profile_begin/end)
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;

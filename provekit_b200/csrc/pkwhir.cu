@@ -114,6 +114,7 @@ void pk_ctx_destroy(pk_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_partials);
     cudaFree(ctx->d_result);
+    if (ctx->d_shard_status) cudaFree(ctx->d_shard_status);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     cudaFree(ctx->d_best);
     cudaFree(ctx->d_twiddles);
@@ -696,6 +697,76 @@ int pk_whir_sumcheck_round(pk_ctx* ctx, const pk_buf* p_in, const pk_buf* w_in, 
                                                     fold ? w_out->d : nullptr, log_n, fold != nullptr, f, ctx->d_partials, ctx->d_result);
     }
     return fetch_result(ctx, out3, 3);
+}
+
+// ---- sharded sumchecks: the round's partial sums are exchanged over peer memory and summed on the device --------------
+size_t pk_shard_mailbox_elems(void) { return SHARD_MAILBOX_BYTES / 32; }
+int pk_shard_group_set(pk_ctx* ctx, int rank, int world, void* const* mailboxes) {
+    PK_BIND(ctx);
+    PK_CHECK(ctx, ctx && mailboxes, "shard_group_set: null argument");
+    PK_CHECK(ctx, world >= 1 && world <= SHARD_MAX_WORLD && (world & (world - 1)) == 0 && rank >= 0 && rank < world,
+             "shard_group_set: world must be a power of two <= %d and 0 <= rank < world", SHARD_MAX_WORLD);
+    for (int i = 0; i < world; i++) PK_CHECK(ctx, mailboxes[i] != nullptr, "shard_group_set: mailbox %d is null", i);
+    if (!ctx->d_shard_status) PK_CUDA(ctx, cudaMalloc((void**)&ctx->d_shard_status, 4));
+    ctx->shard = {};
+    for (int i = 0; i < world; i++) ctx->shard.mbox[i] = (uint8_t*)mailboxes[i];
+    ctx->shard.rank = rank;
+    ctx->shard.world = world;
+    ctx->shard_seq = 0;
+    return PK_OK;
+}
+int pk_shard_group_clear(pk_ctx* ctx) {
+    PK_BIND(ctx);
+    if (!ctx) return PK_ERR_INVALID_ARG;
+    ctx->shard = {};
+    ctx->shard_seq = 0;
+    return PK_OK;
+}
+// result[0..3) on the device -> global sums -> host
+static int exchange_and_fetch(pk_ctx* ctx, uint64_t out3[12]) {
+    PK_CHECK(ctx, ctx->shard.world >= 1, "sharded round without pk_shard_group_set");
+    ctx->launches += launch_shard_exchange(ctx->stream, ctx->d_result, ctx->shard, ++ctx->shard_seq, ctx->d_shard_status);
+    uint32_t status = 0;
+    PK_CUDA(ctx, cudaGetLastError());
+    PK_CUDA(ctx, cudaMemcpyAsync(ctx->h_result, ctx->d_result, 96, cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(ctx, cudaMemcpyAsync(ctx->h_result + 16, ctx->d_shard_status, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::memcpy(out3, ctx->h_result, 96);
+    std::memcpy(&status, ctx->h_result + 16, 4);
+    if (status != 0) return set_err(ctx, PK_ERR_CUDA, "sharded round %u: a peer did not publish its partial sums in time", ctx->shard_seq);
+    return PK_OK;
+}
+int pk_zk_sumcheck_round_sharded(pk_ctx* ctx, pk_buf* a, pk_buf* b, pk_buf* c, pk_buf* eq, int log_n, const uint64_t* fold,
+                                 uint64_t out3[12]) {
+    PK_BIND(ctx);
+    PK_CHECK(ctx, a && b && c && eq && out3, "zk_sumcheck_round_sharded: null argument");
+    PK_CHECK(ctx, log_n >= (fold ? 2 : 1) && log_n < 40, "zk_sumcheck_round_sharded: local size must be >= %d", fold ? 4 : 2);
+    size_t n = (size_t)1 << log_n;
+    PK_CHECK(ctx, a->n >= n && b->n >= n && c->n >= n && eq->n >= n, "zk_sumcheck_round_sharded: arrays shorter than 2^log_n");
+    fr_arg f = {};
+    if (fold) f = to_arg(fold);
+    ProfScope ps(ctx, PROF_ZK_SUMCHECK);
+    ctx->launches += launch_zk_sumcheck_round(ctx->stream, a->d, b->d, c->d, eq->d, log_n, fold != nullptr, f, ctx->d_partials,
+                                              ctx->d_result);
+    return exchange_and_fetch(ctx, out3);
+}
+int pk_whir_sumcheck_round_sharded(pk_ctx* ctx, const pk_buf* p_in, const pk_buf* w_in, pk_buf* p_out, pk_buf* w_out, int log_n,
+                                   const uint64_t* fold, uint64_t out3[12]) {
+    PK_BIND(ctx);
+    PK_CHECK(ctx, p_in && w_in && out3, "whir_sumcheck_round_sharded: null argument");
+    PK_CHECK(ctx, log_n >= (fold ? 2 : 1) && log_n < 40, "whir_sumcheck_round_sharded: local size must be >= %d", fold ? 4 : 2);
+    size_t n = (size_t)1 << log_n;
+    PK_CHECK(ctx, p_in->n >= n && w_in->n >= n, "whir_sumcheck_round_sharded: inputs shorter than 2^log_n");
+    fr_arg f = {};
+    if (fold) {
+        PK_CHECK(ctx, p_out && w_out && p_out->n >= n / 2 && w_out->n >= n / 2, "whir_sumcheck_round_sharded: outputs too small");
+        PK_CHECK(ctx, p_out->d != p_in->d && w_out->d != w_in->d, "whir_sumcheck_round_sharded: folding needs distinct output buffers");
+        f = to_arg(fold);
+    }
+    ProfScope ps(ctx, PROF_WHIR_SUMCHECK);
+    ctx->launches += launch_whir_sumcheck_round(ctx->stream, p_in->d, w_in->d, fold ? p_out->d : nullptr, fold ? w_out->d : nullptr,
+                                                log_n, fold != nullptr, f, ctx->d_partials, ctx->d_result);
+    return exchange_and_fetch(ctx, out3);
 }
 
 // ---- per-kernel-class device timing (CUDA events on the ctx stream) --------------------------------

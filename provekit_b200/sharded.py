@@ -74,8 +74,11 @@ def field_sum(partials: np.ndarray) -> np.ndarray:
 class Gather:
     """all-gather of small uint64 arrays over torch.distributed (nccl on GPUs, gloo in the CPU tests)"""
 
-    def __init__(self, dist=None, device=None):
-        self.dist, self.device = dist, device
+    def __init__(self, dist=None, device=None, group=None):
+        """device: where the collective runs (a cuda device for nccl; None = host tensors, for a gloo group).  The
+        messages are 96 B and already on the host (the C-ABI returns them), so a host-side gloo group next to the NCCL
+        world avoids an H2D + D2H per round."""
+        self.dist, self.device, self.group = dist, device, group
         self.world = dist.get_world_size() if dist is not None else 1
         self.rank = dist.get_rank() if dist is not None else 0
         self.calls = self.bytes = 0
@@ -90,7 +93,7 @@ class Gather:
         if self.device is not None:
             t = t.to(self.device)
         out = torch.empty(self.world * t.numel(), dtype=torch.int64, device=t.device)
-        self.dist.all_gather_into_tensor(out, t)
+        self.dist.all_gather_into_tensor(out, t, group=self.group)
         self.calls += 1
         self.bytes += x.nbytes
         return out.cpu().numpy().view(np.uint64).reshape((self.world,) + x.shape)
@@ -99,11 +102,14 @@ class Gather:
 class GpuBackend:
     """local rounds on this rank's GPU through the C-ABI (pk_zk_sumcheck_round / pk_whir_sumcheck_round)"""
 
-    def __init__(self, ctx):
-        self.ctx = ctx
+    def __init__(self, ctx, fused: bool = False):
+        """fused: the ranks' contexts are joined by pk_shard_group_set; a local round then returns the GLOBAL message
+        (partial sums exchanged by the kernel over NVLink peer stores) and no host-side collective is needed."""
+        self.ctx, self.fused = ctx, fused
 
     def upload(self, arr):
-        return self.ctx.upload(arr)
+        """host array -> new device buffer; a device buffer is adopted as is (the sumcheck folds it in place and frees it)"""
+        return arr if hasattr(arr, "device_ptr") else self.ctx.upload(arr)
 
     def alloc(self, n):
         return self.ctx.buffer(n)
@@ -114,13 +120,16 @@ class GpuBackend:
     def free(self, buf):
         buf.free()
 
-    def zk_round(self, bufs, log_n, fold):
+    def zk_round(self, bufs, log_n, fold, local=False):
+        if self.fused and local:
+            return self.ctx.sumcheck_fold_map_reduce_sharded(*bufs, log_n, fold)
         return self.ctx.sumcheck_fold_map_reduce(*bufs, log_n, fold)
 
-    def whir_round(self, src, dst, log_n, fold):
+    def whir_round(self, src, dst, log_n, fold, local=False):
+        f = self.ctx.whir_sumcheck_round_sharded if (self.fused and local) else self.ctx.whir_sumcheck_round
         if fold is None:
-            return self.ctx.whir_sumcheck_round(src[0], src[1], log_n)
-        return self.ctx.whir_sumcheck_round(src[0], src[1], log_n, fold, dst[0], dst[1])
+            return f(src[0], src[1], log_n)
+        return f(src[0], src[1], log_n, fold, dst[0], dst[1])
 
 
 def sharded_zk_sumcheck(backend, gather: Gather, local_arrays, log_n: int, challenge, rounds: int = None):
@@ -145,10 +154,11 @@ def sharded_zk_sumcheck(backend, gather: Gather, local_arrays, log_n: int, chall
                 backend.free(b)
             bufs = [backend.upload(unshard_low_bits(list(p))) for p in parts]
             cur, local = lg + 1, False
-        part = backend.zk_round(bufs, cur, fold)
+        sharded_round = local and world > 1
+        part = backend.zk_round(bufs, cur, fold, local=sharded_round)
         if fold is not None:
             cur -= 1
-        sums = field_sum(gather(part)) if local and world > 1 else part
+        sums = field_sum(gather(part)) if sharded_round and not getattr(backend, "fused", False) else part
         msgs.append(sums)
         fold = challenge(rnd, sums)
     for b in bufs:
@@ -176,11 +186,12 @@ def sharded_whir_sumcheck(backend, gather: Gather, local_p, local_w, log_n: int,
             src = tuple(backend.upload(unshard_high_bits(list(p))) for p in parts)
             dst = (backend.alloc(world), backend.alloc(world))
             cur, local = lg + 1, False
-        part = backend.whir_round(src, dst, cur, fold)
+        sharded_round = local and world > 1
+        part = backend.whir_round(src, dst, cur, fold, local=sharded_round)
         if fold is not None:
             cur -= 1
             src, dst = dst, src
-        sums = field_sum(gather(part)) if local and world > 1 else part
+        sums = field_sum(gather(part)) if sharded_round and not getattr(backend, "fused", False) else part
         msgs.append(sums)
         fold = challenge(rnd, sums)
     for b in src + dst:

@@ -16,8 +16,81 @@ pytestmark = pytest.mark.gpu
 def test_sharded_sumchecks_match_unsharded(world, log_n):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "tools", "sharded_sumcheck.py"), "--log-n",
-           str(log_n), "--backend", "gloo", "--same-device", "--check", "--steps", "1", "--warmup", "0"]
+           str(log_n), "--backend", "gloo", "--same-device", "--exchange", "gather", "--check", "--steps", "1", "--warmup", "0"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
     assert out.returncode == 0, out.stderr[-3000:]
     r = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert r["messages_match_unsharded"] is True and r["n_gpus"] == world
+
+
+@pytest.mark.parametrize("world,log_n", [(2, 11), (4, 8), (8, 6)])
+def test_fused_exchange_virtual_ranks(world, log_n):
+    """pk_*_round_sharded with the ranks as threads of one process (one ctx / stream each, all on cuda:0, mailboxes are
+    plain device buffers): the kernel-side exchange (peer stores, flag wait, field sum) must reproduce the unsharded
+    messages bit for bit, for both sumchecks."""
+    import hashlib
+    import sys
+    import threading
+
+    import numpy as np
+
+    sys.path.insert(0, ROOT)
+    import provekit_b200 as pk
+    from helpers import rand_fr
+    from provekit_b200 import sharded
+
+    def challenge(rnd, sums):
+        d = hashlib.sha256(bytes([rnd]) + np.ascontiguousarray(sums).tobytes()).digest()
+        return sharded._to_limbs(int.from_bytes(d, "little") % sharded.P).reshape(1, 4)
+
+    class ThreadGather:  # hand-over gather between the threads (the per-round exchange never goes through it)
+        def __init__(self, rank, shared):
+            self.rank, self.world, self.shared, self.calls, self.bytes = rank, world, shared, 0, 0
+
+        def __call__(self, x):
+            self.shared["slots"][self.rank] = np.array(x, copy=True)
+            self.shared["bar"].wait()
+            out = np.stack(self.shared["slots"])
+            self.shared["bar"].wait()
+            return out
+
+    rng = np.random.default_rng(21)
+    arrs = [rand_fr(rng, 1 << log_n) for _ in range(4)]
+    ctxs = [pk.Context(0) for _ in range(world)]
+    boxes = [c.shard_mailbox() for c in ctxs]
+    for r, c in enumerate(ctxs):
+        c.shard_group(r, world, [b.device_ptr for b in boxes])
+    shared = {"slots": [None] * world, "bar": threading.Barrier(world)}
+    results, errors = [None] * world, []
+
+    def run(r):
+        try:
+            be = sharded.GpuBackend(ctxs[r], fused=True)
+            g = ThreadGather(r, shared)
+            zk = sharded.sharded_zk_sumcheck(be, g, [sharded.shard_low_bits(a, r, world) for a in arrs], log_n, challenge)
+            wh = sharded.sharded_whir_sumcheck(be, g, sharded.shard_high_bits(arrs[0], r, world),
+                                               sharded.shard_high_bits(arrs[1], r, world), log_n, challenge)
+            results[r] = (zk, wh)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+            shared["bar"].abort()
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert not errors, errors
+    one = sharded.Gather(None)
+    be0 = sharded.GpuBackend(ctxs[0])
+    zk1 = sharded.sharded_zk_sumcheck(be0, one, arrs, log_n, challenge)
+    wh1 = sharded.sharded_whir_sumcheck(be0, one, arrs[0], arrs[1], log_n, challenge)
+    for r in range(world):
+        zk, wh = results[r]
+        assert len(zk) == log_n and len(wh) == log_n
+        assert all(np.array_equal(x, y) for x, y in zip(zk, zk1)), f"rank {r} zk"
+        assert all(np.array_equal(x, y) for x, y in zip(wh, wh1)), f"rank {r} whir"
+    for b in boxes:
+        b.free()
+    for c in ctxs:
+        c.close()

@@ -60,11 +60,11 @@ class OracleBackend:
     def alloc(self, n): return np.zeros((n, 4), np.uint64)
     def download(self, b, n): return b[:n].copy()
     def free(self, b): pass
-    def zk_round(self, bufs, log_n, fold):
+    def zk_round(self, bufs, log_n, fold, local=False):
         out = np.zeros((3, 4), np.uint64)
         orc.orc_zk_sumcheck_round(*[ptr(b) for b in bufs], log_n, ptr(fold) if fold is not None else None, ptr(out))
         return out
-    def whir_round(self, src, dst, log_n, fold):
+    def whir_round(self, src, dst, log_n, fold, local=False):
         out = np.zeros((3, 4), np.uint64)
         orc.orc_whir_sumcheck_round(ptr(src[0]), ptr(src[1]), log_n, ptr(fold) if fold is not None else None, ptr(out))
         if fold is not None:  # the oracle folds in place; the kernel writes (p_out, w_out)

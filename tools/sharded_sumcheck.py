@@ -36,6 +36,11 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--backend", default="nccl", choices=["nccl", "gloo"])
+    ap.add_argument("--small-collective", default="gloo", choices=["gloo", "nccl"],
+                    help="transport of the 96-byte round messages when the world is NCCL")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "gather"],
+                    help="fused: partial sums exchanged by a kernel over CUDA-IPC peer memory (pk_*_round_sharded); "
+                         "gather: host-side all-gather per round")
     ap.add_argument("--same-device", action="store_true", help="all ranks on cuda:0 (single-GPU box test mode)")
     ap.add_argument("--check", action="store_true", help="rank 0 also runs unsharded and compares every round message")
     args = ap.parse_args()
@@ -49,23 +54,42 @@ def main():
         else:
             dist.init_process_group("gloo")
         d = dist
-    gather = sharded.Gather(d, torch.device("cuda", dev) if (d is not None and args.backend == "nccl") else None)
+    if d is not None and args.backend == "nccl" and args.small_collective == "nccl":
+        gather = sharded.Gather(d, torch.device("cuda", dev))
+    elif d is not None and args.backend == "nccl":
+        gather = sharded.Gather(d, None, group=d.new_group(backend="gloo"))  # 96-byte messages stay on the host
+    else:
+        gather = sharded.Gather(d, None)
     ctx = pk.Context(dev)
-    be = sharded.GpuBackend(ctx)
+    fused = args.exchange == "fused" and world > 1
+    be = sharded.GpuBackend(ctx, fused=fused)
+    peers = []
+    if fused:
+        mbox = ctx.shard_mailbox()
+        handles = [None] * world
+        d.all_gather_object(handles, ctx.ipc_export(mbox))
+        peers = [mbox.device_ptr if r == rank else ctx.ipc_open(handles[r]) for r in range(world)]
+        ctx.shard_group(rank, world, peers)
+        d.barrier()  # every mailbox is zeroed and mapped before the first round
     m0, m = args.log_n, args.log_n + 1
     rng = np.random.default_rng(8)
     zk_full = [rand_fr(rng, 1 << m0) for _ in range(4)]
     wh_full = [rand_fr(rng, 1 << m) for _ in range(2)]
-    zk_loc = [sharded.shard_low_bits(a, rank, world) for a in zk_full]
-    wh_loc = [sharded.shard_high_bits(a, rank, world) for a in wh_full]
+    # the local shards live on the device (in a sharded prover they are produced there); every step folds a fresh clone
+    zk_loc = [ctx.upload(sharded.shard_low_bits(a, rank, world)) for a in zk_full]
+    wh_loc = [ctx.upload(sharded.shard_high_bits(a, rank, world)) for a in wh_full]
     whir_rounds = 4  # one WHIR folding step (FoldingFactor::Constant(4)); afterwards the polynomial is re-committed
 
     def step():
+        zk_in, wh_in = [b.clone() for b in zk_loc], [b.clone() for b in wh_loc]
+        ctx.sync()
+        if d is not None:
+            d.barrier()
         t0 = time.perf_counter()
-        zk = sharded.sharded_zk_sumcheck(be, gather, zk_loc, m0, challenge)
+        zk = sharded.sharded_zk_sumcheck(be, gather, zk_in, m0, challenge)
         ctx.sync()
         t1 = time.perf_counter()
-        wh = sharded.sharded_whir_sumcheck(be, gather, wh_loc[0], wh_loc[1], m, challenge, rounds=whir_rounds)
+        wh = sharded.sharded_whir_sumcheck(be, gather, wh_in[0], wh_in[1], m, challenge, rounds=whir_rounds)
         ctx.sync()
         t2 = time.perf_counter()
         return zk, wh, (t1 - t0) * 1e3, (t2 - t1) * 1e3
@@ -81,7 +105,7 @@ def main():
         wh_ms.append(b)
     ms = np.array([min(zk_ms), min(wh_ms)])
     if d is not None:  # a sharded step takes as long as its slowest rank
-        t = torch.tensor(ms, dtype=torch.float64, device=gather.device if gather.device is not None else "cpu")
+        t = torch.tensor(ms, dtype=torch.float64, device=torch.device("cuda", dev) if args.backend == "nccl" else "cpu")
         d.all_reduce(t, op=d.ReduceOp.MAX)
         ms = t.cpu().numpy()
     ok = None
@@ -95,12 +119,15 @@ def main():
         n0, n1 = 1 << m0, 1 << m
         zk_bytes = 32 * 4 * (n0 + sum(n0 >> (i - 1) for i in range(1, m0)) + sum(n0 >> i for i in range(1, m0)))
         print(json.dumps({"workload": f"sharded sumchecks: zk over 4 x 2^{m0} (all {m0} rounds), WHIR over 2 x 2^{m} ({whir_rounds} rounds)",
-                          "n_gpus": world, "backend": args.backend, "same_device": args.same_device,
+                          "n_gpus": world, "backend": args.backend, "exchange": "fused (NVLink peer stores + device-side sum)" if fused else "host all-gather over " + (args.small_collective if args.backend == "nccl" else "gloo"), "same_device": args.same_device,
                           "zk_sumcheck_ms": float(ms[0]), "whir_sumcheck_ms": float(ms[1]),
                           "zk_alg_gbs": zk_bytes / float(ms[0]) / 1e6,
-                          "includes": "upload of the local shards (H2D) + all rounds + per-round D2H of the message and the all-gather",
+                          "includes": "all rounds with the shards resident in HBM: local kernel, D2H of the 96-byte partial message, all-gather, modular sum, challenge",
                           "exchange": f"{gather.calls} all-gathers, {gather.bytes} B sent per rank in total (96 B per sharded round + 2-element hand-over)",
                           "messages_match_unsharded": ok}))
+    for r, p in enumerate(peers):
+        if r != rank:
+            ctx.ipc_close(p)
     ctx.close()
     if d is not None:
         d.destroy_process_group()
