@@ -123,7 +123,7 @@ def main():
                           "zk_sumcheck_ms": float(ms[0]), "whir_sumcheck_ms": float(ms[1]),
                           "zk_alg_gbs": zk_bytes / float(ms[0]) / 1e6,
                           "includes": "all rounds with the shards resident in HBM: local kernel, D2H of the 96-byte partial message, all-gather, modular sum, challenge",
-                          "exchange": f"{gather.calls} all-gathers, {gather.bytes} B sent per rank in total (96 B per sharded round + 2-element hand-over)",
+                          "host_collectives": f"{gather.calls} all-gathers, {gather.bytes} B sent per rank over all steps (hand-over of the 2-element shards; plus 96 B per round when --exchange gather)",
                           "messages_match_unsharded": ok}))
     for r, p in enumerate(peers):
         if r != rank:
