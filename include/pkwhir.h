@@ -235,6 +235,17 @@ void pk_prover_timings(const pk_prover *p, double out[9]);
 int pk_np_encode(const uint8_t *transcript, size_t len, uint8_t **file_out, size_t *file_len);
 int pk_np_decode(const uint8_t *file, size_t len, uint8_t **transcript_out, size_t *transcript_len);
 
+/* ---- `.nps` scheme container: zstd(postcard(NoirProofScheme)), format tag "NrProScm"
+ * (provekit/common/src/file/mod.rs:27-29, noir_proof_scheme.rs:16-23).  Extracts the R1CS (r1cs.rs:7-13: interner +
+ * three interned-CSR matrices, sparse_matrix.rs:10-27) in exactly the form pk_prover_create consumes (constants converted
+ * to Montgomery form); the ACIR program in front of it and the witness builders behind it are skipped (witness solving
+ * stays on the host, out of scope).  The returned object owns the arrays pk_nps_r1cs points into. */
+typedef struct pk_nps pk_nps;
+int pk_nps_read_r1cs(const uint8_t *file, size_t len, pk_nps **out);
+const pk_r1cs *pk_nps_r1cs(const pk_nps *s);
+int64_t pk_nps_num_public_inputs(const pk_nps *s); /* -1 when not decodable */
+void pk_nps_free(pk_nps *s);
+
 /* ---- measurement: CUDA-event timing per kernel class on the ctx stream (no reference counterpart).
  * Between begin and end every launch group is bracketed by an event pair.  Classes: 0 RS-encode NTT
  * passes, 1 Merkle leaf hashing, 2 Merkle upper levels, 3 zk-sumcheck rounds, 4 WHIR sumcheck rounds,

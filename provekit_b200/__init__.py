@@ -5,4 +5,4 @@ this package is only the host-side harness the tests and bench.py drive it throu
 package never falls back to a CPU implementation: without the built CUDA library `Context()` raises.
 """
 from ._abi import LIB_PATH, PkError, build, lib  # noqa: F401
-from .api import Buffer, Commitment, Context, Prover, np_decode, np_encode  # noqa: F401
+from .api import Buffer, Commitment, Context, Prover, np_decode, np_encode, nps_read_r1cs  # noqa: F401

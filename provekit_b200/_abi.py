@@ -107,6 +107,10 @@ def lib() -> ctypes.CDLL:
         "pk_prover_timings": (None, [vp, POINTER(c_double)]),
         "pk_np_encode": (c_int, [vp, sz, POINTER(vp), POINTER(sz)]),
         "pk_np_decode": (c_int, [vp, sz, POINTER(vp), POINTER(sz)]),
+        "pk_nps_read_r1cs": (c_int, [vp, sz, POINTER(vp)]),
+        "pk_nps_r1cs": (POINTER(R1CS), [vp]),
+        "pk_nps_num_public_inputs": (ctypes.c_int64, [vp]),
+        "pk_nps_free": (None, [vp]),
         "pk_profile_begin": (c_int, [vp]),
         "pk_profile_end": (c_int, [vp, POINTER(c_double), POINTER(c_uint64), POINTER(c_double)]),
         "pk_prover_upload_inputs": (c_int, [vp, u64p, POINTER(Rand)]),

@@ -12,7 +12,7 @@ Names follow the reference:
 Field elements are numpy uint64 arrays of shape (n, 4): arkworks' Montgomery limbs.
 """
 import ctypes
-from ctypes import byref, c_double, c_float, c_size_t, c_uint64, c_void_p
+from ctypes import POINTER, byref, c_double, c_float, c_size_t, c_uint64, c_void_p
 
 import numpy as np
 
@@ -334,6 +334,32 @@ def np_decode(file_bytes: bytes) -> bytes:
     data = ctypes.string_at(out, n.value)
     L.pk_free(out)
     return data
+
+
+def nps_read_r1cs(file_bytes: bytes) -> dict:
+    """bytes of a `.nps` file (NoirProofScheme) -> the R1CS dict Prover takes (pk_nps_read_r1cs): num_constraints,
+    num_witnesses, interned (Montgomery, (k,4) uint64), a/b/c = (row_start u64, col u32, val u32), num_public_inputs."""
+    L = _abi.lib()
+    src = np.frombuffer(file_bytes, dtype=np.uint8)
+    h = c_void_p()
+    rc = L.pk_nps_read_r1cs(_p(src), len(src), byref(h))
+    if rc != 0:
+        raise PkError(rc, "pk_nps_read_r1cs: not a .nps container or no R1CS found in it")
+    r = L.pk_nps_r1cs(h).contents
+
+    def arr(ptr, n, dt):
+        if n == 0:
+            return np.zeros(0, dt)
+        return np.ctypeslib.as_array(ctypes.cast(ptr, POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n,)).copy()
+
+    def csr(m):
+        return (arr(m.row_start, m.num_rows, np.uint64), arr(m.col, m.nnz, np.uint32), arr(m.val, m.nnz, np.uint32))
+
+    out = dict(num_constraints=int(r.num_constraints), num_witnesses=int(r.num_witnesses),
+               interned=arr(r.interned, 4 * r.num_interned, np.uint64).reshape(-1, 4), a=csr(r.a), b=csr(r.b), c=csr(r.c),
+               num_public_inputs=int(L.pk_nps_num_public_inputs(h)))
+    L.pk_nps_free(h)
+    return out
 
 
 class Prover:
