@@ -260,12 +260,8 @@ __device__ __forceinline__ fr fr_mul(const fr& a, const fr& b) {
 
 // canonical integer < p  ->  Montgomery form
 __device__ __forceinline__ fr fr_to_mont(const fr& c) { return fr_mul(c, fr_r2()); }
-// Montgomery form -> canonical integer (multiply by raw 1)
-__device__ __forceinline__ fr fr_from_mont(const fr& a) {
-    fr one = fr_zero();
-    one.v[0] = 1;
-    return fr_mul(a, one);
-}
+// Montgomery form -> canonical integer (reduction rows only, fr_sqr.inc)
+__device__ __forceinline__ fr fr_from_mont(const fr& a) { return fr_redc(a); }
 // any 256-bit value -> [0, p): 2^256 / p < 5.3, so at most 5 subtractions
 __device__ __forceinline__ fr fr_reduce_any(fr a) {
 #pragma unroll 1

@@ -139,76 +139,100 @@ int launch_to_mont(cudaStream_t st, void* data, size_t n, bool to_mont) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K0 wavelet (evaluations <-> coefficients): add/sub butterflies only, HBM bound; tiled in shared
-// memory so a 2^21 vector is 2 passes over HBM instead of 21.
+// K0 wavelet (evaluations <-> coefficients): add/sub butterflies only.  A 2^21 vector is two or three passes over
+// HBM: every pass stages a tile of 2^T elements in shared memory and runs the stages of the index bits the tile spans.
+// One kernel serves both tile shapes:
+//   flat tile : 2^T contiguous elements                                (cbits = T; stages over tile bits [0, T))
+//   row tile  : 2^(T-cbits) rows at stride 2^l x 2^cbits contiguous    (stages over tile bits [cbits, T) = index bits [l, ..))
+// The stage loop is radix-8 in registers: a thread owns the 8 elements that differ in three consecutive stage bits, runs
+// 12 butterflies and writes 7 elements back (element 0 of a group never changes), i.e. 15 shared-memory accesses per
+// three stages instead of 36 and one barrier instead of three -- the radix-2 version was shared-memory-bandwidth bound.
+// Shared layout: split lo/hi planes (SmTile) with the element index XOR-swizzled by its bits [3,6), which makes the
+// stride-8 / stride-64 / ... register-group accesses and the linear load/store phases all bank-conflict free.
 // ------------------------------------------------------------------------------------------------
-constexpr int WAVELET_FLAT_BITS = 11;  // 2^11 x 32 B = 64 KB tile
-constexpr int WAVELET_ROW_BITS = 7;    // 2^7 rows x 16 cols x 32 B = 64 KB tile
+#ifndef PK_WAVELET_TILE_BITS
+#define PK_WAVELET_TILE_BITS 11   // 2^11 x 32 B = 64 KB tile
+#endif
+#ifndef PK_WAVELET_MIN_CBITS
+#define PK_WAVELET_MIN_CBITS 1    // shortest contiguous run of a row tile: 2^1 elements = 64 B
+#endif
+constexpr int WAVELET_TILE_BITS = PK_WAVELET_TILE_BITS;
+constexpr int WAVELET_MIN_CBITS = PK_WAVELET_MIN_CBITS;
+constexpr int WAVELET_THREADS = 256;
+
+static __device__ __forceinline__ int wv_swz(int e) { return e ^ ((e >> 3) & 7); }
+
+template <bool INV, int G>
+static __device__ __forceinline__ void wavelet_group(const SmTile& sm, int T, int hb0) {
+    constexpr int R = 1 << G;
+    const int items = 1 << (T - G);
+    for (int t = threadIdx.x; t < items; t += blockDim.x) {
+        const int e0 = ((t >> hb0) << (hb0 + G)) | (t & ((1 << hb0) - 1));
+        fr x[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) x[j] = sm.get(wv_swz(e0 + (j << hb0)));
+#pragma unroll
+        for (int sbit = 0; sbit < G; sbit++)
+#pragma unroll
+            for (int j = 0; j < R; j++)
+                if (!(j & (1 << sbit))) {
+                    const int hi = j | (1 << sbit);
+                    x[hi] = INV ? fr_sub(x[hi], x[j]) : fr_add(x[hi], x[j]);
+                }
+#pragma unroll
+        for (int j = 1; j < R; j++) sm.put(wv_swz(e0 + (j << hb0)), x[j]);
+    }
+}
 
 template <bool INV>
-__global__ void __launch_bounds__(512) k_wavelet_flat(fr* a, int bits) {
+__global__ void __launch_bounds__(WAVELET_THREADS, 3) k_wavelet_tile(fr* a, int T, int cbits, int l) {
     extern __shared__ uint4 smem_raw[];
-    size_t base = (size_t)blockIdx.x << bits;
-    int n = 1 << bits;
+    const int n = 1 << T;
     SmTile sm(smem_raw, n);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sm.put(i, fr_load(&a[base + i]));
+    const size_t tile = blockIdx.x;
+    const size_t lowgrp = tile & (((size_t)1 << (l - cbits)) - 1);
+    const size_t hi = tile >> (l - cbits);
+    const size_t base = (hi << (l + T - cbits)) | (lowgrp << cbits);
+    const int cmask = (1 << cbits) - 1;
+    for (int e = threadIdx.x; e < n; e += blockDim.x)
+        sm.put(wv_swz(e), fr_load(&a[base + ((size_t)(e >> cbits) << l) + (e & cmask)]));
     __syncthreads();
-    for (int hb = 0; hb < bits; hb++) {
-        int h = 1 << hb;
-        for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
-            int i = ((t >> hb) << (hb + 1)) | (t & (h - 1));
-            fr lo = sm.get(i), hi = sm.get(i + h);
-            sm.put(i + h, INV ? fr_sub(hi, lo) : fr_add(hi, lo));
-        }
+    // INV (evaluations -> coefficients) and forward both commute across stages: any stage order gives the same result
+    for (int hb = (cbits == T ? 0 : cbits); hb < T;) {
+        const int g = T - hb >= 3 ? 3 : T - hb;
+        if (g == 3)
+            wavelet_group<INV, 3>(sm, T, hb);
+        else if (g == 2)
+            wavelet_group<INV, 2>(sm, T, hb);
+        else
+            wavelet_group<INV, 1>(sm, T, hb);
+        hb += g;
         __syncthreads();
     }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) fr_store(&a[base + i], sm.get(i));
-}
-// rows at stride 2^l elements, S row bits, 16 contiguous columns per row
-template <bool INV>
-__global__ void __launch_bounds__(512) k_wavelet_rows(fr* a, int l, int S) {
-    extern __shared__ uint4 smem_raw[];
-    size_t tile = blockIdx.x;
-    size_t lowgrp = tile & (((size_t)1 << (l - 4)) - 1);
-    size_t hi = tile >> (l - 4);
-    size_t base = (hi << (l + S)) | (lowgrp << 4);
-    int rows = 1 << S;
-    SmTile sm(smem_raw, rows * 16);
-    for (int idx = threadIdx.x; idx < rows * 16; idx += blockDim.x)
-        sm.put(idx, fr_load(&a[base + ((size_t)(idx >> 4) << l) + (idx & 15)]));
-    __syncthreads();
-    for (int hb = 0; hb < S; hb++) {
-        int h = 1 << hb;
-        for (int t = threadIdx.x; t < (rows / 2) * 16; t += blockDim.x) {
-            int k = t & 15, b = t >> 4;
-            int i = ((b >> hb) << (hb + 1)) | (b & (h - 1));
-            fr lo = sm.get(i * 16 + k), hiv = sm.get((i + h) * 16 + k);
-            sm.put((i + h) * 16 + k, INV ? fr_sub(hiv, lo) : fr_add(hiv, lo));
-        }
-        __syncthreads();
-    }
-    for (int idx = threadIdx.x; idx < rows * 16; idx += blockDim.x)
-        fr_store(&a[base + ((size_t)(idx >> 4) << l) + (idx & 15)], sm.get(idx));
+    for (int e = threadIdx.x; e < n; e += blockDim.x)
+        fr_store(&a[base + ((size_t)(e >> cbits) << l) + (e & cmask)], sm.get(wv_swz(e)));
 }
 int launch_wavelet(cudaStream_t st, void* a, int log_n, bool inverse) {
     int launches = 0;
-    int flat = log_n < WAVELET_FLAT_BITS ? log_n : WAVELET_FLAT_BITS;
-    size_t smem = ((size_t)32 << flat);
-    unsigned grid = 1u << (log_n - flat);
-    if (inverse)
-        k_wavelet_flat<true><<<grid, 512, smem, st>>>((fr*)a, flat);
-    else
-        k_wavelet_flat<false><<<grid, 512, smem, st>>>((fr*)a, flat);
-    launches++;
-    for (int l = flat; l < log_n;) {
-        int S = (log_n - l) < WAVELET_ROW_BITS ? (log_n - l) : WAVELET_ROW_BITS;
-        size_t sm2 = (size_t)32 * 16 << S;
-        unsigned g2 = 1u << (log_n - S - 4);
+    auto pass = [&](int T, int cbits, int l) {
+        size_t smem = (size_t)32 << T;
+        unsigned grid = 1u << (log_n - T);
+        int threads = (1 << T) / 8 < WAVELET_THREADS ? ((1 << T) / 8 < 32 ? 32 : (1 << T) / 8) : WAVELET_THREADS;
         if (inverse)
-            k_wavelet_rows<true><<<g2, 512, sm2, st>>>((fr*)a, l, S);
+            k_wavelet_tile<true><<<grid, threads, smem, st>>>((fr*)a, T, cbits, l);
         else
-            k_wavelet_rows<false><<<g2, 512, sm2, st>>>((fr*)a, l, S);
+            k_wavelet_tile<false><<<grid, threads, smem, st>>>((fr*)a, T, cbits, l);
         launches++;
+    };
+    const int flat = log_n < WAVELET_TILE_BITS ? log_n : WAVELET_TILE_BITS;
+    pass(flat, flat, flat);
+    // remaining index bits [flat, log_n): as few row passes as the shortest allowed contiguous run permits, balanced
+    const int rest = log_n - flat, max_s = WAVELET_TILE_BITS - WAVELET_MIN_CBITS;
+    const int npass = rest > 0 ? (rest + max_s - 1) / max_s : 0;
+    int l = flat;
+    for (int p = 0; p < npass; p++) {
+        int S = (log_n - l + (npass - p) - 1) / (npass - p);
+        pass(WAVELET_TILE_BITS, WAVELET_TILE_BITS - S, l);
         l += S;
     }
     return launches;
@@ -1010,10 +1034,8 @@ int launch_rng_fill(cudaStream_t st, void* out, size_t n, const uint32_t key[8],
 cudaError_t init_kernel_attributes() {
     cudaError_t e;
     const int smem = 64 * 1024;
-    if ((e = cudaFuncSetAttribute(k_wavelet_flat<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
-    if ((e = cudaFuncSetAttribute(k_wavelet_flat<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
-    if ((e = cudaFuncSetAttribute(k_wavelet_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
-    if ((e = cudaFuncSetAttribute(k_wavelet_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+    if ((e = cudaFuncSetAttribute(k_wavelet_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+    if ((e = cudaFuncSetAttribute(k_wavelet_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
     if ((e = cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, smem + 32768))) return e;
     return cudaSuccess;
 }
