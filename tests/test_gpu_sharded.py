@@ -32,6 +32,9 @@ def test_fused_exchange_virtual_ranks(world, log_n):
     import sys
     import threading
 
+    if os.environ.get("CUDA_LAUNCH_BLOCKING") == "1":
+        pytest.skip("the ranks' exchange kernels must run concurrently")
+
     import numpy as np
 
     sys.path.insert(0, ROOT)
