@@ -51,28 +51,57 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  ONE sampler per job
-    (rank 0) covering the GPUs in use, at 0.5 s period: nvidia-smi takes a driver-wide lock, so a sampler per rank
-    stalls CUDA calls of every process on an 8-GPU box."""
+    """SM clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  ONE sampler per job (rank 0)
+    covering the GPUs in use.  Sampled through NVML in-process (nvidia_ml_py): spawning `nvidia-smi` takes a driver-wide
+    lock that stalls every CUDA call on the box for tens of milliseconds, which showed up as sporadic 10-30 % dips of a
+    200 ms timed region.  Falls back to nvidia-smi (0.5 s period) only when NVML cannot be loaded."""
+
+    REASONS = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, n_gpus=1):
         super().__init__(daemon=True)
         self.n_gpus, self.rows, self._halt = n_gpus, [], threading.Event()
+        self.nvml, self.handles = None, []
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            ids = [int(x) for x in vis.split(",")][:n_gpus] if vis and all(x.strip().isdigit() for x in vis.split(",")) else range(n_gpus)
+            self.handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in ids]
+            self.nvml = pynvml
+            self.bits = [pynvml.nvmlClocksEventReasonHwSlowdown, pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                         pynvml.nvmlClocksEventReasonSwThermalSlowdown, pynvml.nvmlClocksEventReasonSwPowerCap]
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    def _sample_nvml(self):
+        n = self.nvml
+        for h in self.handles:
+            sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+            mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+            rs = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+            self.rows.append([str(sm), str(mx)] + ["Active" if rs & b else "Not Active" for b in self.bits])
+
+    def _sample_smi(self):
         q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                           capture_output=True, text=True, timeout=10).stdout.strip()
+        for ln in o.splitlines():
+            r = [x.strip() for x in ln.split(",")]
+            if len(r) >= 7 and r[0].isdigit() and int(r[0]) < self.n_gpus:
+                self.rows.append(r[1:])
+
+    def run(self):
         while not self._halt.is_set():
             try:
-                o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=10).stdout.strip()
-                for ln in o.splitlines():
-                    r = [x.strip() for x in ln.split(",")]
-                    if len(r) >= 7 and r[0].isdigit() and int(r[0]) < self.n_gpus:
-                        self.rows.append(r[1:])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._halt.wait(0.5)
+            self._halt.wait(0.1 if self.nvml is not None else 0.5)
 
     def finish(self):
         self._halt.set()
@@ -80,10 +109,10 @@ class ClockSampler(threading.Thread):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(self.REASONS) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "sm_min_mhz": sm[0] if sm else None, "reasons": reasons, "samples": len(self.rows)}
+                "sm_min_mhz": sm[0] if sm else None, "reasons": reasons, "samples": len(self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def oracle_structs(r1cs, rnd):
@@ -170,7 +199,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="poseidon-1000", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--in-flight", type=int, default=6,
+    ap.add_argument("--in-flight", type=int, default=8,
                     help="independent proofs in flight per GPU (own ctx/stream/host thread each): the host<->device "
                          "round trips of one proof (~120 challenges) are hidden behind the kernels of the other")
     args = ap.parse_args()
@@ -297,6 +326,8 @@ def main():
     barrier()
     e2e_ms, e2e_wall, proof = run_concurrent(lambda p_: p_.prove_seeded(witness, seed), args.steps)
     barrier()
+    e2e_detail = {"device_ms": e2e_ms, "wall_ms": e2e_wall, "host_stage_s_last_proof": dict(zip(
+        ["commit", "h2d", "zk_sumcheck", "whir_sumcheck", "pow", "open", "spmv_weights", "other", "total"], [round(x, 5) for x in prover.timings()]))}
     e2e_ms = max_over_ranks(max(e2e_ms, e2e_wall))
     # the same with the masks as host arrays (the explicit-mask entry point the parity tests use)
     run_concurrent(lambda p_: p_.prove(witness, rnd_p), n_fl)
@@ -315,6 +346,7 @@ def main():
                      "gpu_launches": int(launches), "clocks": clocks,
                      "e2e": {"value": aggregate_throughput(args.steps, world, e2e_ms), "unit": "proofs/s", "h2d_bytes_per_step": int(h2d),
                              "d2h_bytes_per_step": int(d2h)},
+                     "e2e_detail": e2e_detail,
                      "e2e_host_masks": {"value": aggregate_throughput(args.steps, world, hm_ms), "unit": "proofs/s",
                                         "h2d_bytes_per_step": int(h2d_host_masks), "d2h_bytes_per_step": int(d2h)}})
         # roofline of the dominant kernel: Merkle leaf hashing of the witness commitment (L = 2^(m-3) leaves of 32)

@@ -169,7 +169,7 @@ int pk_whir_sumcheck_round(pk_ctx *ctx, const pk_buf *p_in, const pk_buf *w_in, 
  * stores and adds them up: out3 is the GLOBAL round message on every rank, with no host-side collective.
  *   mailbox: pk_buf_alloc_shared(ctx, pk_shard_mailbox_elems()), zeroed (pk_buf_zero) BEFORE any rank's first round
  *   (barrier in the caller); mailboxes[r] = rank r's mailbox (own device pointer, or pk_ipc_open of the peer's handle).
- * All ranks must call the sharded rounds in lock step; a peer that never arrives -> PK_ERR_CUDA after ~1 s, not a hang.
+ * All ranks must call the sharded rounds in lock step; a peer that never arrives -> PK_ERR_CUDA after ~10 s, not a hang.
  * When a shard is down to two elements the caller gathers the 2G survivors and finishes with the unsharded entry points
  * (host logic: provekit_b200/sharded.py). */
 size_t pk_shard_mailbox_elems(void);

@@ -781,7 +781,7 @@ __global__ void __launch_bounds__(32) k_shard_exchange(fr* result, ShardGroup G,
         const volatile uint32_t* flag = reinterpret_cast<const volatile uint32_t*>(src + 96);
         uint32_t spins = 0;
         while (*flag != seq) {
-            if (++spins > (1u << 24)) {  // ~ a second: a peer never arrived; report instead of hanging the GPU
+            if (++spins > (1u << 27)) {  // ~10 s: a peer never arrived; report instead of hanging the GPU
                 ok = false;
                 break;
             }
@@ -915,7 +915,11 @@ __global__ void __launch_bounds__(128) k_pow_scan(fr_arg challenge, fr_arg thres
     fr r = fr_zero();
     r.v[0] = (uint32_t)nonce;
     r.v[1] = (uint32_t)(nonce >> 32);
-    fr h = sky_compress(l, r);
+    // re-check between round pairs: the nonces in flight when the winner lands stop after at most two more rounds
+    bool done;
+    fr h = sky_compress_while(
+        l, r, [&](int j) { return j == 0 || *reinterpret_cast<volatile unsigned long long*>(best) >= nonce; }, done);
+    if (!done) return;
     fr thr = arg_fr(threshold);
     bool less = false;
 #pragma unroll

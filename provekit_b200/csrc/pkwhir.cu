@@ -315,9 +315,11 @@ int pk_pow_solve(pk_ctx* ctx, const uint64_t challenge[4], double bits, uint64_t
     f64_to_u256(std::exp2(-(bits + 0.01)) * modulus, thr);      // PROVER_BIAS, pow.rs:6,37
     unsigned long long init = ~0ULL;
     PK_CUDA(ctx, cudaMemcpyAsync(ctx->d_best, &init, 8, cudaMemcpyHostToDevice, ctx->stream));
-    // one launch covers ~8x the expected nonce; blocks above the first hit exit immediately (k_pow_scan),
-    // so the cost tracks the winning nonce, not the chunk size
-    uint64_t chunk = (uint64_t)1 << 18;
+    // one launch covers ~8x the expected nonce (miss probability e^-8); blocks above the first hit exit immediately and
+    // nonces in flight are abandoned between round pairs (k_pow_scan), so the cost tracks the winning nonce, not the
+    // chunk size.  Small difficulties (the blinding WHIR's 4..11 bits) get small chunks: a 2^18 floor made every one of
+    // them hash 2^18 nonces, all resident at once, before the early exit could act.
+    uint64_t chunk = (uint64_t)1 << 12;
     double want = std::exp2(bits + 3.0);
     while ((double)chunk < want && chunk < ((uint64_t)1 << 30)) chunk <<= 1;
     for (uint64_t base = 0;; base += chunk) {

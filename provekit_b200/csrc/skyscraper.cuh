@@ -165,10 +165,18 @@ __device__ __forceinline__ fr sky_canon(const fr& x) { return fr_reduce_once(fr_
 // The state is kept lazily reduced in [0, 2p + eps) like the reference does (generic.rs:81-101); only bar
 // canonicalises its input (bar.rs:17) and only the output is fully reduced.  Bounds: fr_sqr_lazy(x) < 1.84p for
 // x < 2.1p, so r + F + rc < 4.9p < 2^256.
-__device__ __forceinline__ fr sky_compress(const fr& l_in, const fr& r_in) {
+// `keep_going(j)` is polled before every pair of rounds; when it returns false the compression is abandoned and `done` is
+// cleared (the PoW scan stops hashing nonces that can no longer win).
+template <class KeepGoing>
+__device__ __forceinline__ fr sky_compress_while(const fr& l_in, const fr& r_in, KeepGoing keep_going, bool& done) {
     fr l = l_in, r = r_in;
+    done = true;
 #pragma unroll 1
     for (int j = 0; j < 9; j++) {
+        if (!keep_going(j)) {
+            done = false;
+            return l;
+        }
         const bool is_bar = (j == 3) | (j == 5);
         if (is_bar) {
             r = sky_reduce_2p(add3_raw(r, sky_bar(sky_canon(l)), sky_rc(2 * j)));
@@ -179,6 +187,10 @@ __device__ __forceinline__ fr sky_compress(const fr& l_in, const fr& r_in) {
         }
     }
     return sky_reduce(add3_raw(l, l_in, fr_zero()));
+}
+__device__ __forceinline__ fr sky_compress(const fr& l_in, const fr& r_in) {
+    bool done;
+    return sky_compress_while(l_in, r_in, [](int) { return true; }, done);
 }
 
 // provekit/common/src/skyscraper/whir.rs:20-25 on Montgomery-form field elements
