@@ -37,6 +37,11 @@ from tools import workload as wl  # noqa: E402
 WORKLOADS = {
     # configs[1]: poseidon-rounds shapes (fixture poseidon-1000.nps): m = 21, m_0 = 20
     "poseidon-1000": wl.POSEIDON_1000,
+    # configs[3]-sized full proof: synthetic R1CS with 2^22 constraints and witnesses (m = 23, m_0 = 22); not the headline
+    "synthetic-2p22": dict(num_constraints=(1 << 22) - 4096, num_witnesses=1 << 22,
+                           nnz=((1 << 22) - 96, (1 << 22) - 104_096, 2 * ((1 << 22) - 4096)), n_interned=64),
+    # a substitute at the size class of configs[2] (noir-examples/sha256 cannot be compiled here: no nargo): m_0 = 18
+    "sha256-substitute": dict(num_constraints=250_000, num_witnesses=300_000, nnz=(400_000, 300_000, 600_000), n_interned=128),
     # small variant for quick checks
     "small": dict(num_constraints=40_000, num_witnesses=50_000, nnz=(41_000, 35_000, 100_000), n_interned=64),
 }
@@ -155,8 +160,9 @@ def base_line(args, workload, r1cs):
         "metric": "noir-r1cs prove proofs/sec (WHIR hot path: RS-encode NTT + Skyscraper Merkle + sumcheck/fold)",
         "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (256-bit BN254-Fr Montgomery)",
-        "data": "synthetic satisfiable R1CS with the shapes of the reference fixture poseidon-1000.nps; masks from a "
-                "32-byte seed (ChaCha12 counter stream, the reference's thread_rng construction)",
+        "data": ("synthetic satisfiable R1CS with the shapes of the reference fixture poseidon-1000.nps" if workload == "poseidon-1000"
+                 else f"synthetic satisfiable R1CS ({workload})") + "; masks from a 32-byte seed (ChaCha12 counter stream, the "
+                "reference's thread_rng construction)",
         "config": {"workload": f"{workload}: {r1cs['num_constraints']} constraints x {r1cs['num_witnesses']} witnesses, "
                                f"m={m}, m_0={m0}, blinding m={mh}, WHIR fold 4, rate 1/2, batch 2, 128-bit ConjectureList",
                    "parallelism": f"proof-level replicas x{args.gpus} (one process per GPU, no data-path collective)",
