@@ -142,6 +142,10 @@ int pk_eval_eq_batch(pk_ctx *ctx, const uint64_t *points, size_t k, int n, const
 int pk_mle_eval(pk_ctx *ctx, const pk_buf *evals, int log_n, const uint64_t *point, uint64_t out[4]);
 /* k <= 3 weight vectors at the same point in one pass (the deferred_weight_evaluations hint) */
 int pk_mle_eval_batch(pk_ctx *ctx, const pk_buf *const *evals, int k, int log_n, const uint64_t *point, uint64_t *out);
+/* the same for arrays known to vanish beyond their first n_prefix elements (the R1CS weight vectors are zero-extended
+ * from #witnesses to 2^m, whir_r1cs.rs:382-412): only the prefix is read */
+int pk_mle_eval_batch_prefix(pk_ctx *ctx, const pk_buf *const *evals, int k, int log_n, size_t n_prefix,
+                             const uint64_t *point, uint64_t *out);
 /* CoefficientList::fold: 2^k consecutive coefficients -> 1; r[j] binds bit j of the in-block index */
 int pk_fold_coeffs(pk_ctx *ctx, const pk_buf *coeffs, int log_n, const uint64_t *r, int k, pk_buf *out);
 

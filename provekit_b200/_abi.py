@@ -87,6 +87,7 @@ def lib() -> ctypes.CDLL:
         "pk_eval_univariate_batch": (c_int, [vp, POINTER(vp), c_int, sz, u64p, u64p]),
         "pk_multi_dot": (c_int, [vp, POINTER(vp), c_int, POINTER(vp), c_int, sz, u64p]),
         "pk_mle_eval_batch": (c_int, [vp, POINTER(vp), c_int, c_int, u64p, u64p]),
+        "pk_mle_eval_batch_prefix": (c_int, [vp, POINTER(vp), c_int, c_int, sz, u64p, u64p]),
         "pk_axpy": (c_int, [vp, vp, vp, u64p, sz]),
         "pk_dot": (c_int, [vp, vp, vp, sz, u64p]),
         "pk_eval_eq": (c_int, [vp, u64p, c_int, u64p, vp]),

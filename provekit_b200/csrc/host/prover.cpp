@@ -231,7 +231,7 @@ class Prover {
     double* T() { return P->timings; }
 
     int batch_commit(int m, pk_buf* masked_evals, pk_buf* g_evals, Commitment* cm, bool timed);
-    int whir_prove(const WhirCfg& cfg, Commitment* cm, pk_buf* const* weights, const Fr* sums, int n_weights);
+    int whir_prove(const WhirCfg& cfg, Commitment* cm, pk_buf* const* weights, const Fr* sums, int n_weights, size_t weights_len);
     int whir_sumcheck_rounds(BufP (&Pb)[2], BufP (&Wb)[2], int* which, int* cur_log, int rounds, Fr* rs, bool* pending,
                              Fr* pending_r);
     int pow_prove(double bits);
@@ -323,9 +323,12 @@ int Prover::whir_sumcheck_rounds(BufP (&Pb)[2], BufP (&Wb)[2], int* which, int* 
 }
 
 // [whir] Prover::prove
-int Prover::whir_prove(const WhirCfg& cfg, Commitment* cm, pk_buf* const* weights, const Fr* sums, int n_weights) {
+// weights_len: the linear weights vanish beyond their first weights_len elements (zero-extended R1CS rows)
+int Prover::whir_prove(const WhirCfg& cfg, Commitment* cm, pk_buf* const* weights, const Fr* sums, int n_weights,
+                       size_t weights_len) {
     const int n = cfg.num_variables;
     const size_t N = (size_t)1 << n;
+    if (weights_len == 0 || weights_len > N) weights_len = N;
     Fr gamma, g = pkh::ONE;
     fs.challenge_scalars(&gamma, 1);
     BufP Pb[2] = {BufP(new Buf(ctx, N)), BufP(new Buf(ctx, N / 2))};
@@ -337,7 +340,7 @@ int Prover::whir_prove(const WhirCfg& cfg, Commitment* cm, pk_buf* const* weight
     PK_TRY(pk_eval_eq(ctx, pt[0].l, n, g.l, *Wb[0]));  // OOD constraint goes first
     for (int j = 0; j < n_weights; j++) {
         g = pkh::mul(g, gamma);
-        PK_TRY(pk_axpy(ctx, *Wb[0], weights[j], g.l, N));
+        PK_TRY(pk_axpy(ctx, *Wb[0], weights[j], g.l, weights_len));
     }
     (void)sums;  // the claimed sum only enters the verifier's checks; h(0), h(1), h(2) are computed directly
     PK_TRY(pk_buf_copy(ctx, *Pb[0], 0, *cm->poly, 0, N));
@@ -471,7 +474,7 @@ int Prover::whir_prove(const WhirCfg& cfg, Commitment* cm, pk_buf* const* weight
     std::vector<uint8_t> hb;
     pkh::put_u64(hb, (uint64_t)n_weights);
     Fr dv[3];
-    PK_TRY(pk_mle_eval_batch(ctx, weights, n_weights, n, R[0].l, dv[0].l));
+    PK_TRY(pk_mle_eval_batch_prefix(ctx, weights, n_weights, n, weights_len, R[0].l, dv[0].l));
     for (int j = 0; j < n_weights; j++) pkh::put_fr(hb, dv[j]);
     fs.hint(hb);
     return PK_OK;
@@ -558,7 +561,7 @@ int Prover::run() {
         Fr stmt = pkh::add(fg[0], pkh::mul(cmh.batching, fg[1]));
         fs.add_scalars(fg, 2);
         pk_buf* ws[1] = {dw};
-        PK_TRY(whir_prove(P->ch, &cmh, ws, &stmt, 1));
+        PK_TRY(whir_prove(P->ch, &cmh, ws, &stmt, 1, 0));
     }
 
     // ---- weights from the R1CS instance: eq(alpha)^T * {A,B,C}, zero-extended to 2^m ----
@@ -594,7 +597,7 @@ int Prover::run() {
         fs.hint(hb);
     }
     pk_buf* ws[3] = {*wts[0], *wts[1], *wts[2]};
-    PK_TRY(whir_prove(P->cw, &cmw, ws, stmts, 3));
+    PK_TRY(whir_prove(P->cw, &cmw, ws, stmts, 3, nw));
     PK_TRY(pk_ctx_sync(ctx));
     T()[8] += now_s() - t_start;
     T()[7] = T()[8] - (T()[0] + T()[1] + T()[2] + T()[3] + T()[4] + T()[5] + T()[6]);

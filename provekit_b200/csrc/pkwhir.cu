@@ -633,8 +633,13 @@ int pk_eval_eq(pk_ctx* ctx, const uint64_t* point, int n, const uint64_t scalar[
     return pk_eval_eq_batch(ctx, point, 1, n, scalar, out);
 }
 int pk_mle_eval_batch(pk_ctx* ctx, const pk_buf* const* evals, int k, int log_n, const uint64_t* point, uint64_t* out) {
+    return pk_mle_eval_batch_prefix(ctx, evals, k, log_n, (size_t)1 << (log_n >= 0 && log_n < 40 ? log_n : 0), point, out);
+}
+int pk_mle_eval_batch_prefix(pk_ctx* ctx, const pk_buf* const* evals, int k, int log_n, size_t n_prefix, const uint64_t* point,
+                             uint64_t* out) {
     PK_BIND(ctx);
     PK_CHECK(ctx, evals && point && out && k >= 1 && k <= 3 && log_n >= 0 && log_n < 40, "mle_eval: bad arguments");
+    PK_CHECK(ctx, n_prefix >= 1 && n_prefix <= ((size_t)1 << log_n), "mle_eval: prefix must be within 2^log_n");
     const void* ptrs[3] = {nullptr, nullptr, nullptr};
     for (int j = 0; j < k; j++) {
         PK_CHECK(ctx, evals[j] && evals[j]->n >= ((size_t)1 << log_n), "mle_eval: array %d too small", j);
@@ -643,7 +648,7 @@ int pk_mle_eval_batch(pk_ctx* ctx, const pk_buf* const* evals, int k, int log_n,
     char *t_hi, *t_lo;
     int lo;
     PK_TRY(build_point_tables(ctx, point, log_n, true, &t_hi, &t_lo, &lo));
-    ctx->launches += launch_multi_tensor_dot(ctx->stream, ptrs, k, (size_t)1 << log_n, t_hi, t_lo, lo, ctx->d_partials, ctx->d_result);
+    ctx->launches += launch_multi_tensor_dot(ctx->stream, ptrs, k, n_prefix, t_hi, t_lo, lo, ctx->d_partials, ctx->d_result);
     return fetch_result(ctx, out, k);
 }
 int pk_mle_eval(pk_ctx* ctx, const pk_buf* evals, int log_n, const uint64_t* point, uint64_t out[4]) {
