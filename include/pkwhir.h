@@ -138,6 +138,12 @@ int pk_multi_dot(pk_ctx *ctx, const pk_buf *const *a, int na, const pk_buf *cons
 int pk_eval_eq(pk_ctx *ctx, const uint64_t *point, int n, const uint64_t scalar[4], pk_buf *out);
 /* several points at once: out[idx] += sum_k scalars[k] * eq(points[k], idx)  (STIR/OOD constraints) */
 int pk_eval_eq_batch(pk_ctx *ctx, const uint64_t *points, size_t k, int n, const uint64_t *scalars, pk_buf *out);
+/* the same sum for UNIVARIATE points on a multiplicative subgroup — the STIR constraints of a WHIR round
+ * (recursive-verifier/app/circuit/whir.go:139-142: z_k = expDomainGen^leafIndex, expanded by ExpandFromUnivariate):
+ * out[x] += sum_k scalars[k] * eq((z_k^(2^(n-1)), .., z_k^2, z_k), x) with z_k = omega_D^(exps[k]), D = 2^log_d the
+ * arkworks 2-adic subgroup.  Large batches are evaluated as M^T(DFT_D(sparse scalars)) in O(D log D) multiplications
+ * instead of k * 2^n (exact arithmetic: bit-identical to pk_eval_eq_batch on the expanded points). */
+int pk_eval_eq_roots_batch(pk_ctx *ctx, const uint64_t *exps, size_t k, int log_d, int n, const uint64_t *scalars, pk_buf *out);
 /* Weights::linear(w).compute(point): sum_idx evals[idx] * eq(point, idx) */
 int pk_mle_eval(pk_ctx *ctx, const pk_buf *evals, int log_n, const uint64_t *point, uint64_t out[4]);
 /* k <= 3 weight vectors at the same point in one pass (the deferred_weight_evaluations hint) */

@@ -92,6 +92,7 @@ def lib() -> ctypes.CDLL:
         "pk_dot": (c_int, [vp, vp, vp, sz, u64p]),
         "pk_eval_eq": (c_int, [vp, u64p, c_int, u64p, vp]),
         "pk_eval_eq_batch": (c_int, [vp, u64p, sz, c_int, u64p, vp]),
+        "pk_eval_eq_roots_batch": (c_int, [vp, u64p, sz, c_int, c_int, u64p, vp]),
         "pk_mle_eval": (c_int, [vp, vp, c_int, u64p, u64p]),
         "pk_fold_coeffs": (c_int, [vp, vp, c_int, u64p, c_int, vp]),
         "pk_zk_sumcheck_round": (c_int, [vp, vp, vp, vp, vp, c_int, u64p, u64p]),

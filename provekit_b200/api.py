@@ -251,6 +251,12 @@ class Context:
         pts, sc = _fe(points), _fe(scalars)
         self._chk(self.L.pk_eval_eq_batch(self.h, _p(pts), len(sc), n, _p(sc), out.h))
 
+    def eval_eq_roots(self, exps, log_d: int, n: int, scalars, out: Buffer):
+        """out[x] += sum_k scalars[k] * eq(pow(omega_D^exps[k]), x) over n variables (pk_eval_eq_roots_batch)"""
+        e = np.ascontiguousarray(exps, dtype=np.uint64)
+        sc = _fe(scalars)
+        self._chk(self.L.pk_eval_eq_roots_batch(self.h, _p(e), len(e), log_d, n, _p(sc), out.h))
+
     def mle_eval(self, evals: Buffer, log_n: int, point) -> np.ndarray:
         out = np.empty(4, np.uint64)
         self._chk(self.L.pk_mle_eval(self.h, evals.h, log_n, _p(_fe(point)), _p(out)))

@@ -440,18 +440,19 @@ int Prover::whir_prove(const WhirCfg& cfg, Commitment* cm, pk_buf* const* weight
                 cur_log--;
                 pending = false;
             }
-            Fr gen = pkh::root_of_unity(domain_log);
-            for (int i = 0; i < FOLD; i++) gen = pkh::sqr(gen);
-            std::vector<Fr> pts((nidx + 1) * (size_t)nvp), sc(nidx + 1);
+            // new equality constraints, scaled by 1, gam, gam^2, ..: the OOD point, then the STIR points
+            // z_q = (domain_gen^16)^idx[q] = omega_D^idx[q] on the folded domain D = 2^(domain_log - 4)
+            // (recursive-verifier/app/circuit/whir.go:139-142).  The STIR batch goes through the sparse-DFT form.
+            std::vector<Fr> pts((size_t)nvp), sc(nidx + 1);
             expand_from_univariate(ood_pt, nvp, pts.data());
             sc[0] = gp;
             for (size_t q = 0; q < nidx; q++) {
                 gp = pkh::mul(gp, gam);
-                expand_from_univariate(pkh::pow_u64(gen, idx[q]), nvp, pts.data() + (q + 1) * nvp);
                 sc[q + 1] = gp;
             }
             // (the folded STIR values only enter the verifier's claimed sum, not the prover's messages)
-            PK_TRY(pk_eval_eq_batch(ctx, pts[0].l, nidx + 1, nvp, sc[0].l, *Wb[which]));
+            PK_TRY(pk_eval_eq(ctx, pts[0].l, nvp, sc[0].l, *Wb[which]));
+            PK_TRY(pk_eval_eq_roots_batch(ctx, idx.data(), nidx, domain_log - FOLD, nvp, sc[1].l, *Wb[which]));
             PK_TRY(whir_sumcheck_rounds(Pb, Wb, &which, &cur_log, FOLD, fold_r, &pending, &pending_r));
             all_r.insert(all_r.end(), fold_r, fold_r + FOLD);
         } else {
@@ -577,10 +578,10 @@ int Prover::run() {
         PK_TRY(pk_buf_zero(ctx, *wts[j], 0, N));
         PK_TRY(spmv(ctx, *T3[j], P->d_interned, eq_alpha.b->d, wts[j]->b->d, nw));
     }
-    {   // the weights vanish beyond the (padded) witness half: N/2 terms suffice for <w_j, f> and <w_j, g>
+    {   // the weights vanish beyond the witness: num_witnesses terms suffice for <w_j, f> and <w_j, g>
         const pk_buf* wa[3] = {*wts[0], *wts[1], *wts[2]};
         const pk_buf* fb[2] = {masked_w, g_w};
-        PK_TRY(pk_multi_dot(ctx, wa, 3, fb, 2, N / 2, fg6[0].l));
+        PK_TRY(pk_multi_dot(ctx, wa, 3, fb, 2, nw, fg6[0].l));
     }
     for (int j = 0; j < 3; j++) {
         f_sums[j] = fg6[2 * j];

@@ -162,7 +162,9 @@ constexpr int WAVELET_THREADS = 256;
 
 static __device__ __forceinline__ int wv_swz(int e) { return e ^ ((e >> 3) & 7); }
 
-template <bool INV, int G>
+// MODE 0: evaluations <- coefficients (hi += lo); 1: coefficients <- evaluations, the Moebius map M (hi -= lo);
+// 2: M transposed (lo -= hi), which maps the monomial weights z^j to the evaluation-basis weights eq(pow(z), x)
+template <int MODE, int G>
 static __device__ __forceinline__ void wavelet_group(const SmTile& sm, int T, int hb0) {
     constexpr int R = 1 << G;
     const int items = 1 << (T - G);
@@ -177,14 +179,18 @@ static __device__ __forceinline__ void wavelet_group(const SmTile& sm, int T, in
             for (int j = 0; j < R; j++)
                 if (!(j & (1 << sbit))) {
                     const int hi = j | (1 << sbit);
-                    x[hi] = INV ? fr_sub(x[hi], x[j]) : fr_add(x[hi], x[j]);
+                    if (MODE == 2)
+                        x[j] = fr_sub(x[j], x[hi]);
+                    else
+                        x[hi] = MODE == 1 ? fr_sub(x[hi], x[j]) : fr_add(x[hi], x[j]);
                 }
+        // the element a stage never touches: index 0 of the group (modes 0/1), index R-1 (mode 2)
 #pragma unroll
-        for (int j = 1; j < R; j++) sm.put(wv_swz(e0 + (j << hb0)), x[j]);
+        for (int j = (MODE == 2 ? 0 : 1); j < (MODE == 2 ? R - 1 : R); j++) sm.put(wv_swz(e0 + (j << hb0)), x[j]);
     }
 }
 
-template <bool INV>
+template <int MODE>
 __global__ void __launch_bounds__(WAVELET_THREADS, 3) k_wavelet_tile(fr* a, int T, int cbits, int l) {
     extern __shared__ uint4 smem_raw[];
     const int n = 1 << T;
@@ -201,27 +207,30 @@ __global__ void __launch_bounds__(WAVELET_THREADS, 3) k_wavelet_tile(fr* a, int 
     for (int hb = (cbits == T ? 0 : cbits); hb < T;) {
         const int g = T - hb >= 3 ? 3 : T - hb;
         if (g == 3)
-            wavelet_group<INV, 3>(sm, T, hb);
+            wavelet_group<MODE, 3>(sm, T, hb);
         else if (g == 2)
-            wavelet_group<INV, 2>(sm, T, hb);
+            wavelet_group<MODE, 2>(sm, T, hb);
         else
-            wavelet_group<INV, 1>(sm, T, hb);
+            wavelet_group<MODE, 1>(sm, T, hb);
         hb += g;
         __syncthreads();
     }
     for (int e = threadIdx.x; e < n; e += blockDim.x)
         fr_store(&a[base + ((size_t)(e >> cbits) << l) + (e & cmask)], sm.get(wv_swz(e)));
 }
-int launch_wavelet(cudaStream_t st, void* a, int log_n, bool inverse) {
+int launch_wavelet(cudaStream_t st, void* a, int log_n, bool inverse) { return launch_wavelet_mode(st, a, log_n, inverse ? 1 : 0); }
+int launch_wavelet_mode(cudaStream_t st, void* a, int log_n, int mode) {
     int launches = 0;
     auto pass = [&](int T, int cbits, int l) {
         size_t smem = (size_t)32 << T;
         unsigned grid = 1u << (log_n - T);
         int threads = (1 << T) / 8 < WAVELET_THREADS ? ((1 << T) / 8 < 32 ? 32 : (1 << T) / 8) : WAVELET_THREADS;
-        if (inverse)
-            k_wavelet_tile<true><<<grid, threads, smem, st>>>((fr*)a, T, cbits, l);
+        if (mode == 2)
+            k_wavelet_tile<2><<<grid, threads, smem, st>>>((fr*)a, T, cbits, l);
+        else if (mode == 1)
+            k_wavelet_tile<1><<<grid, threads, smem, st>>>((fr*)a, T, cbits, l);
         else
-            k_wavelet_tile<false><<<grid, threads, smem, st>>>((fr*)a, T, cbits, l);
+            k_wavelet_tile<0><<<grid, threads, smem, st>>>((fr*)a, T, cbits, l);
         launches++;
     };
     const int flat = log_n < WAVELET_TILE_BITS ? log_n : WAVELET_TILE_BITS;
@@ -647,6 +656,59 @@ int launch_fold_coeffs(cudaStream_t st, const void* coeffs, int log_n, const voi
 }
 
 // ------------------------------------------------------------------------------------------------
+// eq weights of many UNIVARIATE points that are roots of unity (the STIR constraints of a WHIR round):
+//   sum_k s_k eq(pow(z_k), x),  z_k = omega_D^(e_k),   pow(z) = (z^(2^(n-1)), .., z^2, z).
+// In the monomial basis the weight of pow(z) is u_j = z^j, and eq(pow(z), .) = M^T u with M the evaluations->coefficients
+// map, so the whole batch is  M^T ( DFT_D(sparse s)[0 .. 2^n) ):  a sparse scatter, one NTT of size D (the RS-encode
+// kernels at rate 1 plus the radix-16 recombination below) and a transposed wavelet pass -- O(D log D) multiplications
+// instead of 2^n per point.  Field arithmetic is exact, so the result equals the per-point tensor method bit for bit.
+// ------------------------------------------------------------------------------------------------
+// s[e_k] += scalar_k, serially (k is ~100; duplicates of e_k must add up)
+__global__ void k_scatter_add(fr* s, const uint64_t* __restrict__ exps, const fr* __restrict__ scalars, size_t k) {
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (size_t i = 0; i < k; i++) fr_store(&s[exps[i]], fr_add(fr_load(&s[exps[i]]), fr_load_nc(&scalars[i])));
+}
+// u[j] = sum_{c<16} omega_D^(j c) * lv[(j mod D/16) * 16 + c],  j < n_out  (lv: RS-encode leaf layout, leaf i entry c =
+// f_c((omega_D^16)^i) with f_c the stride-16 sub-polynomials): the last radix-16 step of the size-D transform
+__global__ void __launch_bounds__(128) k_dft16_combine(const fr* __restrict__ lv, fr* u, size_t n_out, int log_d,
+                                                       const fr* __restrict__ W, int tbl_shift) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_out) return;
+    const uint32_t D = 1u << log_d, halfD = D >> 1;
+    const fr* row = lv + ((j & ((D >> 4) - 1)) << 4);
+    fr acc = fr_load_nc(&row[0]);
+#pragma unroll 1
+    for (uint32_t c = 1; c < 16; c++) {
+        uint32_t e = ((uint32_t)j * c) & (D - 1);
+        fr t = fr_load_nc(&row[c]);
+        const bool neg = e >= halfD;
+        e &= halfD - 1;
+        if (e) t = fr_mul(t, fr_load_nc(&W[(size_t)e << tbl_shift]));
+        acc = neg ? fr_sub(acc, t) : fr_add(acc, t);
+    }
+    fr_store(&u[j], acc);
+}
+__global__ void __launch_bounds__(256) k_add_inplace(fr* y, const fr* __restrict__ x, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fr_store(&y[i], fr_add(fr_load(&y[i]), fr_load_nc(&x[i])));
+}
+int launch_scatter_add(cudaStream_t st, void* s, const uint64_t* exps, const void* scalars, size_t k) {
+    if (k == 0) return 0;
+    k_scatter_add<<<1, 32, 0, st>>>((fr*)s, exps, (const fr*)scalars, k);
+    return 1;
+}
+int launch_dft16_combine(cudaStream_t st, const void* lv, void* u, size_t n_out, int log_d, const void* table, int table_log_m) {
+    k_dft16_combine<<<(unsigned)((n_out + 127) / 128), 128, 0, st>>>((const fr*)lv, (fr*)u, n_out, log_d, (const fr*)table,
+                                                                   table_log_m - log_d);
+    return 1;
+}
+int launch_add_inplace(cudaStream_t st, void* y, const void* x, size_t n) {
+    if (n == 0) return 0;
+    k_add_inplace<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((fr*)y, (const fr*)x, n);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K5 zk-sumcheck round: fused fold + map + reduce (provekit/common/src/utils/sumcheck.rs:16-104 with
 // the map of provekit/prover/src/whir_r1cs.rs:284-291).  MSB pairing: i <-> i + len/2.
 // ------------------------------------------------------------------------------------------------
@@ -1038,8 +1100,9 @@ int launch_rng_fill(cudaStream_t st, void* out, size_t n, const uint32_t key[8],
 cudaError_t init_kernel_attributes() {
     cudaError_t e;
     const int smem = 64 * 1024;
-    if ((e = cudaFuncSetAttribute(k_wavelet_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
-    if ((e = cudaFuncSetAttribute(k_wavelet_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+    if ((e = cudaFuncSetAttribute(k_wavelet_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+    if ((e = cudaFuncSetAttribute(k_wavelet_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+    if ((e = cudaFuncSetAttribute(k_wavelet_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
     if ((e = cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, smem + 32768))) return e;
     return cudaSuccess;
 }

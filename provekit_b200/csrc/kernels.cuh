@@ -20,6 +20,13 @@ int launch_to_mont(cudaStream_t st, void* data, size_t n, bool to_mont);
 
 // K0 wavelet transforms, in place
 int launch_wavelet(cudaStream_t st, void* a, int log_n, bool inverse);
+// mode 0 forward, 1 inverse (the evaluations->coefficients map M), 2 M transposed (monomial weights -> eq weights)
+int launch_wavelet_mode(cudaStream_t st, void* a, int log_n, int mode);
+// pieces of the sparse-DFT eq-weight batch (see kernels.cu): s[exps[i]] += scalars[i];  u = radix-16 recombination of an
+// RS-encode (rate 1) leaf array into the plain size-2^log_d transform, first n_out outputs;  y += x
+int launch_scatter_add(cudaStream_t st, void* s, const uint64_t* exps, const void* scalars, size_t k);
+int launch_dft16_combine(cudaStream_t st, const void* lv, void* u, size_t n_out, int log_d, const void* table, int table_log_m);
+int launch_add_inplace(cudaStream_t st, void* y, const void* x, size_t n);
 
 // twiddle table W[e] = omega_M^e (Montgomery), e < M/2, omega_M = arkworks 2-adic root of order M = 2^log_m
 // host_pow2: 28 x 8 limbs, omega^(2^b) for b = 0..27 (Montgomery)

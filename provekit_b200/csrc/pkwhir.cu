@@ -628,6 +628,60 @@ int pk_eval_eq_batch(pk_ctx* ctx, const uint64_t* points, size_t k, int n, const
     PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PK_OK;
 }
+// out[x] += sum_k scalars[k] * eq(pow(z_k), x),  z_k = omega_D^(exps[k]), D = 2^log_d  (see kernels.cu, "eq weights of many
+// univariate points").  Small batches fall back to the per-point tensor method on the expanded points.
+int pk_eval_eq_roots_batch(pk_ctx* ctx, const uint64_t* exps, size_t k, int log_d, int n, const uint64_t* scalars, pk_buf* out) {
+    PK_BIND(ctx);
+    PK_CHECK(ctx, exps && scalars && out && n >= 0 && n < 40 && log_d >= 0 && log_d <= 28 && out->n >= ((size_t)1 << n),
+             "eval_eq_roots: bad arguments");
+    if (k == 0) return PK_OK;
+    for (size_t i = 0; i < k; i++) PK_CHECK(ctx, exps[i] < ((uint64_t)1 << log_d), "eval_eq_roots: exponent %zu outside the domain", i);
+    const size_t N = (size_t)1 << n, D = (size_t)1 << log_d;
+    // the transform costs ~ (D/2)(log D - 4) + 15 * 2^n multiplications, the direct method k * 2^n
+    const bool use_dft = n >= 12 && n <= log_d && log_d >= 8 && (double)k * (double)N > 2.0 * (0.5 * D * (log_d - 4) + 16.0 * N);
+    if (!use_dft) {
+        std::vector<uint64_t> pts(k * (size_t)(n > 0 ? n : 1) * 4);
+        pkh::Fr g = pkh::root_of_unity(log_d);
+        for (size_t i = 0; i < k; i++) {
+            pkh::Fr z = pkh::pow_u64(g, exps[i]);
+            for (int v = 0; v < n; v++) {  // expand_from_univariate: point[n-1-v] = z^(2^v)
+                std::memcpy(&pts[(i * n + (n - 1 - v)) * 4], z.l, 32);
+                z = pkh::sqr(z);
+            }
+        }
+        return pk_eval_eq_batch(ctx, pts.data(), k, n, scalars, out);
+    }
+    PK_TRY(ensure_twiddles(ctx, log_d));
+    PK_TRY(ensure_small(ctx, k * 8 + k * 32));
+    char* d_sc = (char*)ctx->d_small;  // 32-byte elements first: they are read with 128-bit loads
+    uint64_t* d_exps = (uint64_t*)((char*)ctx->d_small + k * 32);
+    void *sparse = nullptr, *lv = nullptr;
+    if (cudaMallocAsync(&sparse, D * 32, ctx->stream) != cudaSuccess || cudaMallocAsync(&lv, D * 32, ctx->stream) != cudaSuccess) {
+        if (sparse) cudaFreeAsync(sparse, ctx->stream);
+        return set_err(ctx, PK_ERR_OOM, "eval_eq_roots: out of device memory");
+    }
+    int rc = PK_OK;
+    do {
+        if (cudaMemcpyAsync(d_exps, exps, k * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(d_sc, scalars, k * 32, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemsetAsync(sparse, 0, D * 32, ctx->stream) != cudaSuccess) {
+            rc = set_err(ctx, PK_ERR_CUDA, "eval_eq_roots: staging failed");
+            break;
+        }
+        ctx->launches += launch_scatter_add(ctx->stream, sparse, d_exps, d_sc, k);
+        if ((rc = rs_encode_raw(ctx, sparse, log_d, 0, 4, lv, 16, 0)) != PK_OK) break;
+        // u overwrites the (consumed) sparse vector, then M^T in place, then out += u
+        ctx->launches += launch_dft16_combine(ctx->stream, lv, sparse, N, log_d, ctx->d_twiddles, ctx->twiddle_log_m);
+        ctx->launches += launch_wavelet_mode(ctx->stream, sparse, n, 2);
+        ctx->launches += launch_add_inplace(ctx->stream, out->d, sparse, N);
+        if (cudaGetLastError() != cudaSuccess) rc = set_err(ctx, PK_ERR_CUDA, "eval_eq_roots: launch failed");
+    } while (0);
+    cudaFreeAsync(sparse, ctx->stream);
+    cudaFreeAsync(lv, ctx->stream);
+    if (rc != PK_OK) return rc;
+    PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host arrays may be reused by the caller right away
+    return PK_OK;
+}
 int pk_eval_eq(pk_ctx* ctx, const uint64_t* point, int n, const uint64_t scalar[4], pk_buf* out) {
     PK_BIND(ctx);
     return pk_eval_eq_batch(ctx, point, 1, n, scalar, out);

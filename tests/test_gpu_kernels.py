@@ -383,3 +383,31 @@ def test_merkle_combine_roots(ctx, orc):
         assert np.array_equal(nd.download(1, 1)[0], sub[r])
         leaves.free()
         nd.free()
+
+
+@pytest.mark.parametrize("log_d,n,k", [(18, 17, 109), (14, 13, 81), (13, 12, 300), (12, 12, 401), (17, 13, 300), (14, 13, 40), (9, 5, 31)])
+def test_eval_eq_roots_equals_per_point_method(ctx, log_d, n, k):
+    """pk_eval_eq_roots_batch (STIR constraint weights as M^T of a sparse DFT, or its small-batch fallback) == pk_eval_eq_batch
+    on the expanded points z_k = omega_D^e_k -> (z^(2^(n-1)), .., z^2, z) (ExpandFromUnivariate,
+    recursive-verifier/app/utilities/utilities.go:182-190), bit for bit; duplicates among the e_k must add up."""
+    ROOT28 = 19103219067921713944291392827692070036145651957329286315305642004821462161904  # arkworks TWO_ADIC_ROOT_OF_UNITY
+    w = pow(ROOT28, 1 << (28 - log_d), P)
+    rng = np.random.default_rng(1000 * log_d + n)
+    exps = rng.integers(0, 1 << log_d, size=k, dtype=np.uint64)
+    exps[1] = exps[0]  # a repeated point
+    scal = rng_fr(77 + k, k)
+    pts = []
+    for e in exps:
+        z = pow(w, int(e), P)
+        col = []
+        for _ in range(n):
+            col.append(z)
+            z = z * z % P
+        pts.extend(reversed(col))
+    base = rng_fr(5, 1 << n)
+    a, b = ctx.upload(base), ctx.upload(base)
+    ctx.eval_eq(to_mont(pts), scal, n, a)
+    ctx.eval_eq_roots(exps, log_d, n, scal, b)
+    assert np.array_equal(a.download(), b.download())
+    a.free()
+    b.free()
