@@ -205,8 +205,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="poseidon-1000", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--in-flight", type=int, default=8,
-                    help="independent proofs in flight per GPU (own ctx/stream/host thread each): the host<->device "
+    ap.add_argument("--in-flight", type=int, default=0,
+                    help="independent proofs in flight per GPU, 0 = auto (own ctx/stream/host thread each): the host<->device "
                          "round trips of one proof (~120 challenges) are hidden behind the kernels of the other")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -245,7 +245,12 @@ def main():
         rnd_p[k], t_ = pin(v)
         keep.append(t_)
 
-    n_fl = max(1, args.in_flight)
+    # default: up to 8 proofs in flight, chosen so that the K timed proofs split evenly over the workers (an uneven split
+    # leaves the GPU half empty while the last worker finishes)
+    n_fl = args.in_flight
+    if n_fl <= 0:
+        even = [f for f in range(8, 3, -1) if args.steps % f == 0]
+        n_fl = even[0] if even else min(8, max(1, args.steps))
     ctxs = [pk.Context(local_rank) for _ in range(n_fl)]
     provers = [pk.Prover(c, r1cs) for c in ctxs]
     streams = [torch.cuda.ExternalStream(c.stream) for c in ctxs]
