@@ -17,7 +17,11 @@ def test_sharded_sumchecks_match_unsharded(world, log_n):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "tools", "sharded_sumcheck.py"), "--log-n",
            str(log_n), "--backend", "gloo", "--same-device", "--exchange", "gather", "--check", "--steps", "1", "--warmup", "0"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    for attempt in range(2):  # the rendezvous port is picked, released and re-bound by torchrun: retry once if it was taken
+        cmd[cmd.index("--master-port") + 1] = str(free_port())
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
+        if out.returncode == 0:
+            break
     assert out.returncode == 0, out.stderr[-3000:]
     r = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert r["messages_match_unsharded"] is True and r["n_gpus"] == world
