@@ -108,7 +108,8 @@ class ClockSampler(threading.Thread):
                     self._sample_smi()
             except Exception:
                 pass
-            self._halt.wait(0.1 if self.nvml is not None else 0.5)
+            # constant query rate whatever the GPU count (every NVML query briefly locks its device)
+            self._halt.wait(0.1 * self.n_gpus if self.nvml is not None else 0.5)
 
     def finish(self):
         self._halt.set()
@@ -217,8 +218,14 @@ def main():
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
 
-    import torch
     import provekit_b200 as pk
+    from tools.dist_util import env_rank
+    # PK_BLOCKING_SYNC=1: host threads sleep instead of spinning while they wait for the device (has to be set before torch
+    # creates the CUDA context).  Off by default: measured on a B200 box it costs ~170 us per round trip (one proof in
+    # flight 12.7 -> 34 ms, 135 -> 87 proofs/s); only for hosts with far fewer cores than waiting threads.
+    _, world_, local_ = env_rank()
+    blocking = os.environ.get("PK_BLOCKING_SYNC", "") == "1" and pk.lib().pk_set_blocking_sync(local_, 1) == 0
+    import torch
     from tools.dist_util import Dist, aggregate_throughput
     dd = Dist()
     rank, world, local_rank = dd.rank, dd.world, dd.local_rank
@@ -368,6 +375,8 @@ def main():
         line = base_line(args, args.workload, r1cs)
         value = aggregate_throughput(args.steps, world, dev_ms)
         line["config"]["in_flight_proofs_per_gpu"] = n_fl
+        line["config"]["host_wait"] = "blocking sync" if blocking else "spin (CUDA default)"
+        line["config"]["host_cores"] = os.cpu_count()
         line["config"]["timing"] = (f"value and e2e: best of {REPEATS} timed repetitions of exactly K = {args.steps} steps each "
                                     "(CUDA events; e2e additionally bounded below by host wall clock), max over ranks")
         line.update({"value": value, "ms_per_step": dev_ms / args.steps, "ms_per_step_one_in_flight": single_ms / args.steps,

@@ -42,6 +42,9 @@ typedef struct pk_buf pk_buf;
 typedef struct pk_commitment pk_commitment;
 
 /* ---- context ------------------------------------------------------------------------------- */
+/* optional, BEFORE the first CUDA call on `device` in this process: host threads waiting for the device sleep
+ * (cudaDeviceScheduleBlockingSync) instead of spinning — for many proofs in flight on many GPUs of one box */
+int pk_set_blocking_sync(int device, int on);
 int pk_ctx_create(int device, pk_ctx **out);
 void pk_ctx_destroy(pk_ctx *ctx);
 const char *pk_last_error(const pk_ctx *ctx);

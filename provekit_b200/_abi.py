@@ -50,6 +50,7 @@ def lib() -> ctypes.CDLL:
     L = ctypes.CDLL(LIB_PATH)
     vp, sz, u64p = c_void_p, c_size_t, c_void_p
     sig = {
+        "pk_set_blocking_sync": (c_int, [c_int, c_int]),
         "pk_ctx_create": (c_int, [c_int, POINTER(vp)]),
         "pk_ctx_destroy": (None, [vp]),
         "pk_last_error": (c_char_p, [vp]),

@@ -82,6 +82,20 @@ extern "C" {
 
 const char* pk_version(void) { return "pkwhir 0.1 (sm_100a)"; }
 
+// Host threads that wait for the device (every challenge round trip does) either spin or sleep.  Spinning is the CUDA
+// default and the fastest for one proof; with many proofs in flight on many GPUs of one box the spinning threads can
+// outnumber the cores.  Must be called before the device's primary context exists (before any other CUDA call on it).
+int pk_set_blocking_sync(int device, int on) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return PK_ERR_NO_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return PK_ERR_CUDA;
+    cudaError_t e = cudaSetDeviceFlags(on ? cudaDeviceScheduleBlockingSync : cudaDeviceScheduleAuto);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return PK_ERR_CUDA;  // the primary context is already active: too late for this process
+    }
+    return PK_OK;
+}
 int pk_ctx_create(int device, pk_ctx** out) {
     if (!out) return PK_ERR_INVALID_ARG;
     *out = nullptr;
