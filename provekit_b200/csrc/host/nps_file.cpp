@@ -44,7 +44,7 @@ const uint8_t MAGIC[8] = {0xDC, 0xDF, 'O', 'Z', 'k', 'p', 0x01, 0x00};
 const char FORMAT_NPS[9] = "NrProScm";
 
 bool zstd_inflate(const uint8_t* src, size_t len, std::vector<uint8_t>& out) {
-    void* h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_LOCAL);
+    static void* h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_LOCAL);  // once per process (thread-safe static init)
     if (!h) return false;
     auto createDStream = (void* (*)())dlsym(h, "ZSTD_createDStream");
     auto initDStream = (size_t(*)(void*))dlsym(h, "ZSTD_initDStream");
