@@ -239,6 +239,13 @@ class Context:
         self._chk(self.L.pk_mle_eval_batch(self.h, arr, len(evals_list), log_n, _p(_fe(point)), _p(out)))
         return out
 
+    def mle_eval_batch_prefix(self, evals_list, log_n: int, n_prefix: int, point) -> np.ndarray:
+        """mle_eval_batch for arrays that vanish beyond their first n_prefix elements (only the prefix is read)"""
+        arr = (c_void_p * len(evals_list))(*[p.h for p in evals_list])
+        out = np.empty((len(evals_list), 4), np.uint64)
+        self._chk(self.L.pk_mle_eval_batch_prefix(self.h, arr, len(evals_list), log_n, n_prefix, _p(_fe(point)), _p(out)))
+        return out
+
     def axpy(self, y: Buffer, x: Buffer, a, n: int):
         self._chk(self.L.pk_axpy(self.h, y.h, x.h, _p(_fe(a)), n))
 

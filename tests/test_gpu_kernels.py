@@ -411,3 +411,31 @@ def test_eval_eq_roots_equals_per_point_method(ctx, log_d, n, k):
     assert np.array_equal(a.download(), b.download())
     a.free()
     b.free()
+
+
+@pytest.mark.parametrize("log_n,n_prefix", [(12, 1), (12, 2500), (12, 4096), (17, 70001)])
+def test_mle_eval_prefix_equals_full_on_zero_extended_arrays(ctx, log_n, n_prefix):
+    """pk_mle_eval_batch_prefix reads only the first n_prefix elements; on arrays that are zero beyond them (the
+    zero-extended R1CS weight vectors, whir_r1cs.rs:382-412) it must equal pk_mle_eval_batch; errors on a bad prefix."""
+    from provekit_b200 import PkError
+    n = 1 << log_n
+    arrs = []
+    for k in range(3):
+        a = rng_fr(300 + 10 * log_n + k, n)
+        a[n_prefix:] = 0
+        arrs.append(a)
+    dev = [ctx.upload(a) for a in arrs]
+    point = rng_fr(9, log_n)
+    full = ctx.mle_eval_batch(dev, log_n, point)
+    assert np.array_equal(ctx.mle_eval_batch_prefix(dev, log_n, n_prefix, point), full)
+    # poison the tail: the prefix variant must not look at it
+    for d, a in zip(dev, arrs):
+        b = a.copy()
+        b[n_prefix:] = rng_fr(1, n - n_prefix) if n_prefix < n else b[n_prefix:]
+        d.upload(b)
+    assert np.array_equal(ctx.mle_eval_batch_prefix(dev, log_n, n_prefix, point), full)
+    for bad in (0, n + 1):
+        with pytest.raises(PkError):
+            ctx.mle_eval_batch_prefix(dev, log_n, bad, point)
+    for d in dev:
+        d.free()
