@@ -11,8 +11,12 @@ import numpy as np
 P = 21888242871839275222246405745257275088548364400416034343698204186575808495617
 R = (1 << 256) % P
 
+# `structure` reproduces the fixture's sparsity extremes as well (pk_nps_read_r1cs on poseidon-1000.nps, session 4): A has
+# two rows of 65 536 entries and two columns used 65 537 times, B one column used 131 076 times, C one column used
+# 598 479 times; 120 122 / 120 120 rows of A / B are empty.  These drive the long-row and hot-column SpMV kernels.
 POSEIDON_1000 = dict(num_constraints=729_560, num_witnesses=860_637, nnz=(740_508, 609_440, 1_915_568),
-                     n_interned=366)
+                     n_interned=366,
+                     structure=dict(long_rows=((2, 65_536), ()), hot_cols=(((65_537, 65_537)), (131_076,)), c_hot=598_479))
 
 
 def log2ceil(n: int) -> int:
@@ -56,7 +60,7 @@ def _row_counts(rng, rows, nnz, minimum=0):
     return cnt
 
 
-def synth_r1cs(num_constraints, num_witnesses, nnz, n_interned=366, seed=1):
+def synth_r1cs(num_constraints, num_witnesses, nnz, n_interned=366, seed=1, structure=None):
     rng = np.random.default_rng(seed)
     nc, nw = num_constraints, num_witnesses
     K = nw - nc
@@ -67,10 +71,24 @@ def synth_r1cs(num_constraints, num_witnesses, nnz, n_interned=366, seed=1):
     free[0], free[1] = 1, 0
     mats = []
     az = []
+    st = structure or {}
     for which, n_entries in enumerate(nnz[:2]):
-        cnt = _row_counts(rng, nc, n_entries)
+        long_spec = (st.get("long_rows") or ((), ()))[which]
+        n_long, long_len = long_spec if long_spec else (0, 0)
+        cnt = _row_counts(rng, nc, n_entries - n_long * long_len)
+        if n_long:  # a few very long rows (the fixture's lookup-sum constraints); the rest of the entries stay spread out
+            rows = rng.choice(nc, size=n_long, replace=False)
+            cnt[rows] += long_len
         row_start = np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.uint64)
         col = rng.integers(0, K, size=n_entries, dtype=np.uint32)
+        hot = (st.get("hot_cols") or ((), ()))[which]
+        if hot:  # columns used by tens of thousands of rows: positions drawn among the short rows' entries
+            short = np.flatnonzero(np.repeat(cnt, cnt) <= 64)
+            picks = rng.choice(short, size=int(sum(hot)), replace=False)
+            off = 0
+            for h_i, uses in enumerate(hot):
+                col[picks[off:off + uses]] = 2 + h_i
+                off += uses
         val = rng.integers(0, n_interned, size=n_entries, dtype=np.uint32)
         prod = interned[val] * free[col]
         sums = np.zeros(nc, dtype=object)
@@ -82,12 +100,22 @@ def synth_r1cs(num_constraints, num_witnesses, nnz, n_interned=366, seed=1):
         mats.append((row_start, col, val))
     cnt = _row_counts(rng, nc, nnz[2], minimum=1)
     row_start = np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.uint64)
-    col = np.ones(nnz[2], dtype=np.uint32)                       # surplus entries hit the zero witness
+    col = np.ones(nnz[2], dtype=np.uint32)                       # surplus entries hit the zero witness ...
     val = rng.integers(0, n_interned, size=nnz[2], dtype=np.uint32)
-    col[row_start.astype(np.int64)] = (K + np.arange(nc)).astype(np.uint32)
-    val[row_start.astype(np.int64)] = 0                          # interned[0] = 1
+    first = row_start.astype(np.int64)
+    surplus = np.ones(nnz[2], dtype=bool)
+    surplus[first] = False
+    if st.get("c_hot") is not None:                              # ... or, with `structure`, one hot column and random free ones
+        idx = np.flatnonzero(surplus)
+        spread = rng.choice(idx, size=max(0, len(idx) - int(st["c_hot"])), replace=False)
+        col[spread] = rng.integers(0, K, size=len(spread), dtype=np.uint32)
+    col[first] = (K + np.arange(nc)).astype(np.uint32)
+    val[first] = 0                                               # interned[0] = 1
     mats.append((row_start, col, val))
-    witness = np.concatenate([free, (az[0] * az[1]) % P])
+    # the product witness of row i absorbs the surplus terms of C's row i: w = Az * Bz - sum(surplus coefficients * z)
+    extra = np.where(surplus, interned[val] * free[np.minimum(col, K - 1)], 0)
+    extra_row = np.add.reduceat(extra, first) % P
+    witness = np.concatenate([free, (az[0] * az[1] - extra_row) % P])
     return dict(num_constraints=nc, num_witnesses=nw, interned=to_mont(interned), a=mats[0], b=mats[1], c=mats[2],
                 witness=to_mont(witness))
 
