@@ -114,3 +114,47 @@ def test_reference_fixture_r1cs():
     for k in "abc":
         rs, col, val = got[k]
         assert rs[0] == 0 and np.all(np.diff(rs.astype(np.int64)) >= 0) and int(col.max()) < got["num_witnesses"] and int(val.max()) < 366
+
+
+def _extremes(r):
+    out = {}
+    for k in "abc":
+        rs, col, _ = r[k]
+        cnt = np.diff(np.append(rs.astype(np.int64), len(col)))
+        cc = np.bincount(col, minlength=r["num_witnesses"])
+        out[k] = dict(nnz=len(col), row_max=int(cnt.max()), long_rows=int((cnt > 64).sum()), empty=int((cnt == 0).sum()),
+                      col_max=int(cc.max()), hot_cols=int((cc > 64).sum()))
+    return out
+
+
+def test_synthetic_workload_has_the_fixture_sparsity_extremes():
+    """bench.py's synthetic poseidon-1000 R1CS (tools/workload.py) is satisfiable and has the long rows / hot columns /
+    empty rows of the real scheme; in the build container it is compared with the fixture itself."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from tools import workload as wl
+    r = wl.synth_r1cs(**wl.POSEIDON_1000, seed=1)
+    ex = _extremes(r)
+    assert ex["a"]["long_rows"] == 2 and 65_536 <= ex["a"]["row_max"] <= 65_540 and ex["a"]["hot_cols"] == 2
+    assert ex["b"]["row_max"] == 1 and ex["b"]["hot_cols"] == 1 and 131_076 <= ex["b"]["col_max"] <= 131_090
+    assert ex["c"]["hot_cols"] == 1 and 598_479 <= ex["c"]["col_max"] <= 598_500
+    # satisfiable: (A z) * (B z) == C z on the long rows and a sample of the others
+    rinv = pow(1 << 256, P - 2, P)
+    z = [v * rinv % P for v in arr_to_ints(r["witness"])]
+    iv = [v * rinv % P for v in arr_to_ints(r["interned"])]
+
+    def row_dot(m, i):
+        rs, col, val = m
+        s, e = int(rs[i]), int(rs[i + 1]) if i + 1 < len(rs) else len(col)
+        return sum(iv[val[k]] * z[col[k]] for k in range(s, e)) % P
+
+    cnt_a = np.diff(np.append(r["a"][0].astype(np.int64), len(r["a"][1])))
+    rows = [int(i) for i in np.argsort(cnt_a)[-2:]] + list(range(0, r["num_constraints"], 9973))
+    assert all(row_dot(r["a"], i) * row_dot(r["b"], i) % P == row_dot(r["c"], i) for i in rows)
+    if os.path.exists(REF_NPS):
+        real = _extremes(pk.nps_read_r1cs(open(REF_NPS, "rb").read()))
+        for k in "abc":
+            assert ex[k]["nnz"] == real[k]["nnz"] and ex[k]["long_rows"] == real[k]["long_rows"] and ex[k]["hot_cols"] <= real[k]["hot_cols"]
+            assert abs(ex[k]["col_max"] - real[k]["col_max"]) <= 16
+            assert abs(ex[k]["row_max"] - real[k]["row_max"]) <= (4 if real[k]["long_rows"] else 16)
+            assert abs(ex[k]["empty"] - real[k]["empty"]) <= 16
