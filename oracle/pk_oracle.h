@@ -8,8 +8,12 @@
  * PARITY STATUS: Skyscraper/PoW pinned by the reference KATs (skyscraper/core/src/reference.rs:100-188);
  * Merkle layout, MultiPath encoding, leaf order, RS-encode layout, transcript framing and WHIR
  * parameters pinned by the reference-produced proof fixture (tests/golden/);
- * verifier algebra pinned by the in-tree Go verifier (recursive-verifier/app/circuit/ *.go files).
- * Fiat-Shamir challenge VALUES (spongefish internals, whir label strings): parity unpinned.
+ * verifier algebra restated from the in-tree Go verifier (recursive-verifier/app/circuit/ *.go files) AND pinned against
+ * the reference-produced proof without any Fiat-Shamir layer (tests/test_fixture_algebra.py: challenges recovered as roots
+ * of the sumcheck links; sumcheck message formats, fold order, RS-encode + batch layout on a complete codeword, wavelet /
+ * masked-polynomial layout, OOD, batching, the blinding scheme, and the full verifier equations of the blinding WHIR and
+ * of the zk-sumcheck all hold for exactly one candidate tuple).
+ * Fiat-Shamir challenge DERIVATION (spongefish internals, whir label strings): parity unpinned.
  *
  * Field elements cross this API as arkworks' in-memory form: 4 x u64 little-endian limbs,
  * Montgomery form (R = 2^256), unless a parameter says "canonical".

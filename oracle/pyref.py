@@ -6,6 +6,10 @@ cpu_baseline leg may import this module.  The product path (provekit_b200/) neve
 Python integers mod p are unambiguous, so this file is the *root* of the parity chain:
     reference KATs / fixture  ->  pyref (this file)  ->  oracle C library  ->  CUDA kernels.
 
+The conventions of the [EXT] functions below (fold order, eq / MLE index order, coefficient<->evaluation transform,
+RS-encode leaf layout, univariate OOD evaluation) are additionally pinned by the reference-produced proof itself,
+sponge-free: tests/test_fixture_algebra.py.
+
 Every function cites the reference file:line it follows (paths relative to /root/reference).
 Functions whose algorithm lives in an un-vendored dependency are marked [EXT] and cite the
 in-tree call site / Go restatement that pins them.
