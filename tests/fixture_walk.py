@@ -109,9 +109,10 @@ def walk_whir(rd: Reader, cfg: dict):
     return out
 
 
-def walk_proof(m=21, m_0=20):
-    """proof := commit(W) commit(H) zk-sumcheck whir(H) hint claimed_evaluations whir(W)."""
-    b = open(GOLDEN, "rb").read()
+def walk_proof(m=21, m_0=20, data=None):
+    """proof := commit(W) commit(H) zk-sumcheck whir(H) hint claimed_evaluations whir(W).
+    data: transcript bytes to walk (default: the reference-produced fixture)."""
+    b = open(GOLDEN, "rb").read() if data is None else data
     rd = Reader(b)
     cfg_w = o.whir_config(m)
     blind_vars = (4 * m_0 - 1).bit_length() + 1

@@ -88,7 +88,7 @@ def test_final_fold_pins_fold_order_and_final_polynomial(proof):
     blk, fin = w["rounds"][3]["sumcheck"], w["final_sumcheck"]
     cands = [quad_link(blk[i - 1], blk[i]) for i in range(1, 4)] + [quad_link(blk[3], fin[0])]
     leaves, idx, fc = w["final_answers"], w["final_multipath"][3], w["final_coeffs"]
-    assert len(leaves) == 9 and len(fc) == 2
+    assert 5 <= len(leaves) <= 9 and len(fc) == 2                # 9 final queries, de-duplicated (9 in the fixture)
     gen = pow(o.root_of_unity(18), 16, P)
     pts = [pow(gen, i, P) for i in idx]
     fits = []
@@ -135,7 +135,7 @@ def test_intermediate_round_answers_fold_into_the_next_committed_polynomial(proo
     f3 = [(leaves[0][k] - hi[k] * y0) % P for k in range(16)] + hi
     rd = w["rounds"][3]
     ans, qidx = rd["answers"], rd["multipath"][3]
-    assert len(ans) == 11 and all(len(a) == 16 for a in ans)
+    assert 8 <= len(ans) <= 11 and all(len(a) == 16 for a in ans)  # 11 queries, de-duplicated (11 in the fixture)
     g19 = pow(o.root_of_unity(19), 16, P)
     target = [o.eval_univariate(f3, pow(g19, i, P)) for i in qidx]
     blk3, blk4 = w["rounds"][2]["sumcheck"], w["rounds"][3]["sumcheck"]
@@ -226,7 +226,7 @@ def test_blinding_commitment_is_fully_checkable(proof):
     assert o.eval_coeffs_at_point(F, o.expand_from_univariate(z, 8)) == a_f      # the multilinear reading of the same point
     # batching + first fold
     fl = h["final_answers"]
-    assert len(fl) == 13 and all(x == fl[0] for x in fl) and len(fl[0]) == 16
+    assert 8 <= len(fl) <= 16 and all(x == fl[0] for x in fl) and len(fl[0]) == 16   # 31 queries on 16 leaves (13 distinct in the fixture)
     cp = fl[0]
     init = h["initial_sumcheck"]
     cands = [quad_link(init[i - 1], init[i]) for i in range(1, 4)]
@@ -487,3 +487,44 @@ def test_zk_sumcheck_verifier_equation_holds_without_the_sponge(proof):
     dfs(0, 1, [])
     assert len(hits) == 1
     assert o.eq_poly_outside(hits[0], alphas) == target
+
+
+# ---- the same sponge-free relations on a proof produced by THIS repository's prover ----------------------------------
+@pytest.fixture(scope="module")
+def own_proof():
+    """A proof of the synthetic poseidon-1000 workload by the CPU oracle prover (the GPU prover's output is byte-identical
+    to it: tests/test_gpu_full_size.py), walked with the same layout code as the reference's proof."""
+    import ctypes
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import oracle
+    from tools import workload as wl
+    oracle.build()
+    orc = oracle.lib()
+    r1cs = wl.synth_r1cs(**wl.POSEIDON_1000, seed=11)
+    for seed in range(5, 25):
+        rnd = wl.randomness(r1cs, seed=seed)    # must outlive the call: the structs only hold pointers into these arrays
+        cs, rs = bench.oracle_structs(r1cs, rnd)
+        _, proof = bench.cpu_prove_once(orc, cs, rs, r1cs["witness"])
+        buf = (ctypes.c_uint8 * len(proof)).from_buffer_copy(proof)
+        assert orc.orc_verify(ctypes.byref(cs), buf, ctypes.c_size_t(len(proof)), 2) == 0
+        walked = fw.walk_proof(data=proof)
+        # the complete-codeword checks need the 122 blinding queries to hit all 32 leaves (they do in ~half of all proofs,
+        # and in the reference fixture); other masks give another transcript
+        if walked["whir_h"]["rounds"][0]["multipath"][3] == list(range(32)):
+            return walked
+    pytest.skip("no proof with a completely opened blinding commitment among 20 mask seeds")
+
+
+def test_own_proof_satisfies_the_relations_pinned_on_the_reference_proof(own_proof):
+    """Closes the loop fixture -> conventions -> our bytes: the proof our prover emits passes the very same sponge-free
+    checks (same functions, same layout walk) that pin the conventions on the reference-produced proof."""
+    test_zk_sumcheck_messages_chain(own_proof)
+    for which in ("whir_h", "whir_w"):
+        test_whir_sumcheck_messages_chain(own_proof, which)
+    test_final_fold_pins_fold_order_and_final_polynomial(own_proof)
+    test_intermediate_round_answers_fold_into_the_next_committed_polynomial(own_proof)
+    test_blinding_commitment_is_fully_checkable(own_proof)
+    test_blinding_whir_final_equation_holds_without_the_sponge(own_proof)
