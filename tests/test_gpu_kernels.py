@@ -43,6 +43,8 @@ def test_compress_many_vs_oracle(ctx, orc, n):
     rng = np.random.default_rng(n)
     msgs = rng.integers(0, 1 << 64, size=(n, 8), dtype=np.uint64)  # arbitrary 256-bit values (>= p allowed)
     edge = [0, (1 << 256) - 1, P - 1, P, 2 * P, P + 1, 5 * P, 5 * P + 12345, 1 << 255]
+    # skyscraper/core/src/reduce.rs:86-96,112-124 (test_reduce_partial_max): low limbs all ones, top limb = top limb of k*p + 1
+    edge += [((((k * P) >> 192) + 1) << 192) | ((1 << 192) - 1) for k in range(6)]
     for i, e in enumerate(edge[:n]):
         msgs[i, :4] = ints_to_arr([e])[0]
         msgs[i, 4:] = ints_to_arr([edge[-1 - i]])[0]
