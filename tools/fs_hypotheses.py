@@ -8,7 +8,11 @@ or split OOD answers, PoW before/after the STIR squeeze, hint order, byte counts
 hashing it into the IV (unpadded Keccak duplex, Keccak-256, SHA3-256), both Skyscraper permutations (v2 and the
 10-round v1 the fixture's Merkle tree uses), both state orders and both IV endiannesses.
 
-Result (r01 session 4): 9 984 strings x 2 permutations x 4 state variants, no match -- the fixture's transcript was built
+Also tried by hand with the same tester: a byte-oriented Keccak duplex transcript (spongefish's DefaultHash; scalars
+absorbed as 32 bytes, challenges from 47/48/32 squeezed bytes, big- or little-endian), and additive instead of
+overwriting absorption / eager permutation after a full rate.
+
+Result (r01 session 4): 9 984 strings x 2 permutations x 4 state variants (+ the families above), no match -- the fixture's transcript was built
 from a domain separator this restatement does not reproduce; the sources (spongefish, whir @ the fixture's revision) are
 needed.  Run:  python tools/fs_hypotheses.py
 """
