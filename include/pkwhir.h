@@ -180,8 +180,10 @@ int pk_whir_sumcheck_round(pk_ctx *ctx, const pk_buf *p_in, const pk_buf *w_in, 
  * sharded round is the single-GPU kernel on the local shard followed by ONE one-warp kernel that stores the three
  * partial sums into every peer's mailbox (CUDA-IPC mapped peer memory, NVLink P2P stores), waits for the peers'
  * stores and adds them up: out3 is the GLOBAL round message on every rank, with no host-side collective.
- *   mailbox: pk_buf_alloc_shared(ctx, pk_shard_mailbox_elems()), zeroed (pk_buf_zero) BEFORE any rank's first round
- *   (barrier in the caller); mailboxes[r] = rank r's mailbox (own device pointer, or pk_ipc_open of the peer's handle).
+ *   mailbox: pk_buf_alloc_shared(ctx, pk_shard_mailbox_elems()); mailboxes[r] = rank r's mailbox (own device pointer, or
+ *   pk_ipc_open of the peer's handle).  pk_shard_group_set wipes the rank's OWN mailbox and restarts the sequence at 0, so a
+ *   mailbox can serve group after group; the caller puts a barrier between group_set and the first round.  After a
+ *   timeout the group is disabled on that rank until the next pk_shard_group_set (the sequence numbers are out of step).
  * All ranks must call the sharded rounds in lock step; a peer that never arrives -> PK_ERR_CUDA after ~10 s, not a hang.
  * When a shard is down to two elements the caller gathers the 2G survivors and finishes with the unsharded entry points
  * (host logic: provekit_b200/sharded.py). */
@@ -221,6 +223,11 @@ typedef struct pk_prover pk_prover;
 /* uploads the R1CS once (scheme-time work, like reading the .nps) */
 int pk_prover_create(pk_ctx *ctx, const pk_r1cs *r1cs, pk_prover **out);
 void pk_prover_destroy(pk_prover *p);
+/* scheme shapes (provekit/r1cs-compiler/src/whir_r1cs.rs:15-36): the witness passed to pk_prove must hold exactly
+ * r1cs.num_witnesses elements (the reference asserts witness.len() == r1cs.num_witnesses(), whir_r1cs.rs:48-54) and the
+ * pk_rand arrays 2^(m-1), 2^m, 4*m_0, 2^(mh-1), 2^mh elements: the library reads exactly that many and cannot check a
+ * bare pointer, so callers size their buffers from these numbers */
+void pk_prover_shapes(const pk_prover *p, int *m, int *m0, int *mh);
 /* returns the spongefish NARG string (= WhirR1CSProof.transcript); *out is malloc'd, free with pk_free */
 int pk_prove(pk_prover *p, const uint64_t *witness, const pk_rand *rnd, uint8_t **out, size_t *out_len);
 /* the two halves of pk_prove, exposed so that a caller can keep one proof's inputs resident in HBM:
@@ -236,6 +243,26 @@ int pk_prove_staged(pk_prover *p, uint8_t **out, size_t *out_len);
 int pk_rng_fill(pk_ctx *ctx, pk_buf *dst, size_t off, size_t n, const uint8_t seed[32], uint32_t stream);
 int pk_prover_upload_inputs_seeded(pk_prover *p, const uint64_t *witness, const uint8_t seed[32]);
 int pk_prove_seeded(pk_prover *p, const uint64_t *witness, const uint8_t seed[32], uint8_t **out, size_t *out_len);
+/* ---- the host's own Fiat-Shamir transcript: WhirR1CSProver::prove with every transcript operation forwarded to the
+ * caller.  The table is exactly the spongefish ProverState surface the reference uses on this path
+ * (provekit/prover/src/whir_r1cs.rs:240-242 challenge_scalars, :268-272 add_scalars + challenge_scalars, :335-337,
+ * :92 hint; [whir] add_digest = add_scalars(1), challenge_pow = challenge_bytes(32) + add_bytes(8 BE nonce),
+ * stir queries = challenge_bytes; IO pattern provekit/common/src/whir_r1cs.rs:28-39): the Rust host passes trampolines
+ * over its `ProverState<SkyscraperSponge, FieldElement>` and keeps sponge, codecs, domain separator and
+ * the proof string (`narg_string()`) on its side, so the bytes are the reference's own by construction.  pk_prove /
+ * pk_prove_seeded are this entry point with the in-tree C++ sponge as the transcript.
+ * Scalars cross as Montgomery 4 x u64; `hint` receives the ark-serialised payload WITHOUT the u32 length prefix
+ * (= `ProverState::hint_bytes`).  Callbacks return 0 on success; any other value aborts the proof with
+ * PK_ERR_INVALID_ARG.  They are called on the calling thread, in protocol order. */
+typedef struct {
+    int (*add_scalars)(void *user, const uint64_t *scalars, size_t n);
+    int (*challenge_scalars)(void *user, uint64_t *out, size_t n);
+    int (*add_bytes)(void *user, const uint8_t *bytes, size_t n);
+    int (*challenge_bytes)(void *user, uint8_t *out, size_t n);
+    int (*hint)(void *user, const uint8_t *payload, size_t n);
+} pk_transcript_vtbl;
+int pk_prove_with_transcript(pk_prover *p, const uint64_t *witness, const pk_rand *rnd, const pk_transcript_vtbl *vt, void *user);
+int pk_prove_staged_with_transcript(pk_prover *p, const pk_transcript_vtbl *vt, void *user);
 void pk_free(void *p);
 /* host wall-clock seconds per stage of the last pk_prove: [0] witness commit (NTT+Merkle), [1] H2D staging of the inputs,
  * [2] zk-sumcheck, [3] WHIR sumcheck rounds, [4] PoW, [5] STIR openings, [6] R1CS mat-vec + weights,

@@ -89,11 +89,36 @@ typedef struct {
     const uint64_t *mask_h;   /* 2^(mh-1) */
     const uint64_t *g_h;      /* 2^mh */
 } orc_rand;
+/* The spongefish ProverState / VerifierState surface the path uses (provekit/prover/src/whir_r1cs.rs:240-242,268-272,
+ * 335-337; provekit/common/src/whir_r1cs.rs:28-39), as callbacks: same shape as pk_transcript_vtbl of include/pkwhir.h
+ * (prover entries) plus the three verifier-side reads.  Scalars are Montgomery 4 x u64.  0 = ok. */
+typedef struct {
+    int (*add_scalars)(void *user, const uint64_t *scalars, size_t n);
+    int (*challenge_scalars)(void *user, uint64_t *out, size_t n);
+    int (*add_bytes)(void *user, const uint8_t *bytes, size_t n);
+    int (*challenge_bytes)(void *user, uint8_t *out, size_t n);
+    int (*hint)(void *user, const uint8_t *payload, size_t n);
+    /* verifier only */
+    int (*next_scalars)(void *user, uint64_t *out, size_t n);
+    int (*next_bytes)(void *user, uint8_t *out, size_t n);
+    int (*next_hint)(void *user, const uint8_t **payload, size_t *n); /* payload stays valid until the next call */
+} orc_transcript_vtbl;
 /* returns transcript length written to *out (malloc'd; free with orc_free), <0 on error */
 int64_t orc_prove(const orc_r1cs *r1cs, const uint64_t *witness, const orc_rand *rnd, int hash_version,
                   uint8_t **out);
 /* 0 = accept; negative = first failed check */
 int orc_verify(const orc_r1cs *r1cs, const uint8_t *transcript, size_t len, int hash_version);
+/* the same prover / verifier with every transcript operation forwarded to the caller (the proof string lives on the
+ * caller's side): 0 = ok / accept */
+int orc_prove_with_transcript(const orc_r1cs *r1cs, const uint64_t *witness, const orc_rand *rnd, int hash_version,
+                              const orc_transcript_vtbl *vt, void *user);
+int orc_verify_with_transcript(const orc_r1cs *r1cs, int hash_version, const orc_transcript_vtbl *vt, void *user);
+/* the in-tree sponge as a foreign transcript: state for the scheme's domain separator (prover: proof == NULL;
+ * verifier: wraps `proof`), its vtable (user = the state), the proof string accumulated so far */
+void *orc_fs_create(uint64_t num_constraints, uint64_t num_witnesses, const uint8_t *proof, size_t proof_len);
+const orc_transcript_vtbl *orc_fs_vtbl(void);
+const uint8_t *orc_fs_narg(const void *fs, size_t *len);
+void orc_fs_free(void *fs);
 void orc_free(void *p);
 /* stage timers of the last orc_prove on this thread, seconds: [commit_w_ntt, commit_w_merkle,
  * zk_sumcheck, whir_sumcheck, pow, other, total] */

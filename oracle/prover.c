@@ -550,7 +550,9 @@ static void batch_commit(fs_state *fs, int m, const fr_t *f_evals /* 2^(m-1) */,
     *g_evals = ge;
 }
 
-int64_t orc_prove(const orc_r1cs *r1cs, const uint64_t *witness_in, const orc_rand *rnd, int hv, uint8_t **out) {
+/* vt == NULL: the in-tree sponge (proof string returned in *out); otherwise the caller's transcript */
+static int64_t prove_impl(const orc_r1cs *r1cs, const uint64_t *witness_in, const orc_rand *rnd, int hv, uint8_t **out,
+                          const orc_transcript_vtbl *vt, void *user) {
     memset(T, 0, sizeof T);
     double t_start = now_s();
     /* scheme shapes: provekit/r1cs-compiler/src/whir_r1cs.rs:15-36 */
@@ -561,11 +563,15 @@ int64_t orc_prove(const orc_r1cs *r1cs, const uint64_t *witness_in, const orc_ra
     whir_cfg cw, ch;
     whir_cfg_new(&cw, m, 2);
     whir_cfg_new(&ch, mh, 2);
-    bytebuf ds = {0};
-    build_domsep(&ds, &cw, &ch, m0);
     fs_state fs;
-    fs_init(&fs, ds.p, ds.len, NULL, 0);
-    free(ds.p);
+    if (vt) {
+        fs_init_foreign(&fs, vt, user, 0);
+    } else {
+        bytebuf ds = {0};
+        build_domsep(&ds, &cw, &ch, m0);
+        fs_init(&fs, ds.p, ds.len, NULL, 0);
+        free(ds.p);
+    }
 
     const fr_t *witness = (const fr_t *)witness_in;
     size_t half = (size_t)1 << (m - 1), N = (size_t)1 << m, N0 = (size_t)1 << m0;
@@ -680,9 +686,18 @@ int64_t orc_prove(const orc_r1cs *r1cs, const uint64_t *witness_in, const orc_ra
     free(g_h);
     commitment_free(&cmw);
     commitment_free(&cmh);
-    *out = fs.narg.p;
     T[6] = now_s() - t_start;
+    if (vt) return fs.failed ? -2 : 0;
+    *out = fs.narg.p;
     return (int64_t)fs.narg.len;
+}
+int64_t orc_prove(const orc_r1cs *r1cs, const uint64_t *witness_in, const orc_rand *rnd, int hv, uint8_t **out) {
+    return prove_impl(r1cs, witness_in, rnd, hv, out, NULL, NULL);
+}
+int orc_prove_with_transcript(const orc_r1cs *r1cs, const uint64_t *witness, const orc_rand *rnd, int hv,
+                              const orc_transcript_vtbl *vt, void *user) {
+    if (!vt || !vt->add_scalars || !vt->challenge_scalars || !vt->add_bytes || !vt->challenge_bytes || !vt->hint) return -1;
+    return (int)prove_impl(r1cs, witness, rnd, hv, NULL, vt, user);
 }
 
 /* ================================ verifier ================================================= */
@@ -983,18 +998,23 @@ static int whir_verify(fs_state *fs, const whir_cfg *cfg, const parsed_commitmen
     return rc;
 }
 
-int orc_verify(const orc_r1cs *r1cs, const uint8_t *transcript, size_t len, int hv) {
+static int verify_impl(const orc_r1cs *r1cs, const uint8_t *transcript, size_t len, int hv, const orc_transcript_vtbl *vt,
+                       void *user) {
     int m = next_pow2_log(r1cs->num_witnesses) + 1;
     int m0 = next_pow2_log(r1cs->num_constraints);
     int mh = next_pow2_log(4 * (uint64_t)m0) + 1;
     whir_cfg cw, ch;
     whir_cfg_new(&cw, m, 2);
     whir_cfg_new(&ch, mh, 2);
-    bytebuf ds = {0};
-    build_domsep(&ds, &cw, &ch, m0);
     fs_state fs;
-    fs_init(&fs, ds.p, ds.len, transcript, len);
-    free(ds.p);
+    if (vt) {
+        fs_init_foreign(&fs, vt, user, 1);
+    } else {
+        bytebuf ds = {0};
+        build_domsep(&ds, &cw, &ch, m0);
+        fs_init(&fs, ds.p, ds.len, transcript, len);
+        free(ds.p);
+    }
     /* provekit/verifier/src/whir_r1cs.rs:40-100 and circuit.go:43-82 */
     parsed_commitment pcw, pch;
     parse_commitment(&fs, 2, &pcw);
@@ -1078,8 +1098,52 @@ int orc_verify(const orc_r1cs *r1cs, const uint8_t *transcript, size_t len, int 
             free(col);
         }
     }
-    if (!rc && (fs.failed || fs.rd != len)) rc = -15;
+    if (!rc && (fs.failed || (!vt && fs.rd != len))) rc = -15; /* a foreign transcript checks its own end of input */
     free(r);
     free(alpha);
     return rc;
+}
+/* ---- the in-tree sponge packaged as a foreign transcript (tests: the product driven by the oracle's transcript
+ * through pk_prove_with_transcript must reproduce orc_prove byte for byte) ---- */
+static int ft_add_scalars(void *u, const uint64_t *x, size_t n) { fs_add_scalars((fs_state *)u, (const fr_t *)x, n); return 0; }
+static int ft_challenge_scalars(void *u, uint64_t *o, size_t n) { fs_challenge_scalars((fs_state *)u, (fr_t *)o, n); return 0; }
+static int ft_add_bytes(void *u, const uint8_t *b, size_t n) { fs_add_bytes((fs_state *)u, b, n); return 0; }
+static int ft_challenge_bytes(void *u, uint8_t *o, size_t n) { fs_challenge_bytes((fs_state *)u, o, n); return 0; }
+static int ft_hint(void *u, const uint8_t *b, size_t n) { fs_hint((fs_state *)u, b, n); return 0; }
+static int ft_next_scalars(void *u, uint64_t *o, size_t n) { fs_next_scalars((fs_state *)u, (fr_t *)o, n); return ((fs_state *)u)->failed; }
+static int ft_next_bytes(void *u, uint8_t *o, size_t n) { fs_next_bytes((fs_state *)u, o, n); return ((fs_state *)u)->failed; }
+static int ft_next_hint(void *u, const uint8_t **p, size_t *n) { *p = fs_next_hint((fs_state *)u, n); return ((fs_state *)u)->failed; }
+const orc_transcript_vtbl *orc_fs_vtbl(void) {
+    static const orc_transcript_vtbl vt = {ft_add_scalars, ft_challenge_scalars, ft_add_bytes, ft_challenge_bytes, ft_hint,
+                                           ft_next_scalars, ft_next_bytes, ft_next_hint};
+    return &vt;
+}
+void *orc_fs_create(uint64_t num_constraints, uint64_t num_witnesses, const uint8_t *proof, size_t proof_len) {
+    int m = next_pow2_log(num_witnesses) + 1, m0 = next_pow2_log(num_constraints);
+    int mh = next_pow2_log(4 * (uint64_t)m0) + 1;
+    whir_cfg cw, ch;
+    whir_cfg_new(&cw, m, 2);
+    whir_cfg_new(&ch, mh, 2);
+    bytebuf ds = {0};
+    build_domsep(&ds, &cw, &ch, m0);
+    fs_state *fs = (fs_state *)malloc(sizeof *fs);
+    fs_init(fs, ds.p, ds.len, proof, proof_len);
+    free(ds.p);
+    return fs;
+}
+const uint8_t *orc_fs_narg(const void *fs, size_t *len) {
+    *len = ((const fs_state *)fs)->narg.len;
+    return ((const fs_state *)fs)->narg.p;
+}
+void orc_fs_free(void *p) {
+    fs_state *fs = (fs_state *)p;
+    if (fs && !fs->is_verifier) free(fs->narg.p);
+    free(fs);
+}
+int orc_verify(const orc_r1cs *r1cs, const uint8_t *transcript, size_t len, int hv) {
+    return verify_impl(r1cs, transcript, len, hv, NULL, NULL);
+}
+int orc_verify_with_transcript(const orc_r1cs *r1cs, int hv, const orc_transcript_vtbl *vt, void *user) {
+    if (!vt || !vt->next_scalars || !vt->challenge_scalars || !vt->next_bytes || !vt->challenge_bytes || !vt->next_hint) return -1;
+    return verify_impl(r1cs, NULL, 0, hv, vt, user);
 }

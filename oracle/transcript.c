@@ -98,11 +98,27 @@ void fs_init(fs_state *fs, const uint8_t *domsep, size_t domsep_len, const uint8
         fs->narg.len = proof_len;
     }
 }
+void fs_init_foreign(fs_state *fs, const orc_transcript_vtbl *vt, void *user, int is_verifier) {
+    memset(fs, 0, sizeof *fs);
+    fs->vt = vt;
+    fs->user = user;
+    fs->is_verifier = is_verifier;
+}
+#define FS_FOREIGN(call)                 \
+    do {                                 \
+        if ((call) != 0) fs->failed = 1; \
+        return;                          \
+    } while (0)
 void fs_add_scalars(fs_state *fs, const fr_t *x, size_t n) {
+    if (fs->vt) FS_FOREIGN(fs->vt->add_scalars(fs->user, (const uint64_t *)x, n));
     sponge_absorb(&fs->sp, x, n);
     for (size_t i = 0; i < n; i++) bb_fr(&fs->narg, x[i]);
 }
 void fs_next_scalars(fs_state *fs, fr_t *x, size_t n) {
+    if (fs->vt) {
+        memset(x, 0, n * sizeof(fr_t));
+        FS_FOREIGN(fs->vt->next_scalars(fs->user, (uint64_t *)x, n));
+    }
     for (size_t i = 0; i < n; i++) {
         if (fs->rd + 32 > fs->narg.len) {
             fs->failed = 1;
@@ -117,8 +133,18 @@ void fs_next_scalars(fs_state *fs, fr_t *x, size_t n) {
     }
     sponge_absorb(&fs->sp, x, n);
 }
-void fs_challenge_scalars(fs_state *fs, fr_t *out, size_t n) { sponge_squeeze(&fs->sp, out, n); }
+void fs_challenge_scalars(fs_state *fs, fr_t *out, size_t n) {
+    if (fs->vt) {
+        memset(out, 0, n * sizeof(fr_t));
+        FS_FOREIGN(fs->vt->challenge_scalars(fs->user, (uint64_t *)out, n));
+    }
+    sponge_squeeze(&fs->sp, out, n);
+}
 void fs_challenge_bytes(fs_state *fs, uint8_t *out, size_t n) {
+    if (fs->vt) {
+        memset(out, 0, n);
+        FS_FOREIGN(fs->vt->challenge_bytes(fs->user, out, n));
+    }
     while (n) {
         fr_t u;
         uint64_t c[4];
@@ -131,6 +157,7 @@ void fs_challenge_bytes(fs_state *fs, uint8_t *out, size_t n) {
     }
 }
 void fs_add_bytes(fs_state *fs, const uint8_t *b, size_t n) {
+    if (fs->vt) FS_FOREIGN(fs->vt->add_bytes(fs->user, b, n));
     for (size_t i = 0; i < n; i++) {
         fr_t u = fr_from_u64(b[i]);
         sponge_absorb(&fs->sp, &u, 1);
@@ -138,6 +165,10 @@ void fs_add_bytes(fs_state *fs, const uint8_t *b, size_t n) {
     bb_push(&fs->narg, b, n);
 }
 void fs_next_bytes(fs_state *fs, uint8_t *b, size_t n) {
+    if (fs->vt) {
+        memset(b, 0, n);
+        FS_FOREIGN(fs->vt->next_bytes(fs->user, b, n));
+    }
     if (fs->rd + n > fs->narg.len) {
         fs->failed = 1;
         memset(b, 0, n);
@@ -151,11 +182,22 @@ void fs_next_bytes(fs_state *fs, uint8_t *b, size_t n) {
     }
 }
 void fs_hint(fs_state *fs, const uint8_t *b, size_t n) {
+    if (fs->vt) FS_FOREIGN(fs->vt->hint(fs->user, b, n));
     uint32_t len = (uint32_t)n;
     bb_push(&fs->narg, &len, 4);
     bb_push(&fs->narg, b, n);
 }
 const uint8_t *fs_next_hint(fs_state *fs, size_t *n) {
+    if (fs->vt) {
+        const uint8_t *p = NULL;
+        *n = 0;
+        if (fs->vt->next_hint(fs->user, &p, n) != 0 || (!p && *n)) {
+            fs->failed = 1;
+            *n = 0;
+            return NULL;
+        }
+        return p;
+    }
     if (fs->rd + 4 > fs->narg.len) {
         fs->failed = 1;
         *n = 0;

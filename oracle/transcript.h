@@ -62,7 +62,12 @@ typedef struct {
     bytebuf narg;          /* prover: grows; verifier: wraps the proof */
     size_t rd;             /* verifier read cursor */
     int is_verifier, failed;
+    /* foreign transcript (orc_prove_with_transcript / orc_verify_with_transcript): every operation is forwarded to the
+     * caller's ProverState / VerifierState instead of the in-tree sponge; a non-zero return marks the run failed */
+    const orc_transcript_vtbl *vt;
+    void *user;
 } fs_state;
+void fs_init_foreign(fs_state *fs, const orc_transcript_vtbl *vt, void *user, int is_verifier);
 void fs_init(fs_state *fs, const uint8_t *domsep, size_t domsep_len, const uint8_t *proof, size_t proof_len);
 void fs_add_scalars(fs_state *fs, const fr_t *x, size_t n);         /* prover */
 void fs_next_scalars(fs_state *fs, fr_t *x, size_t n);              /* verifier */

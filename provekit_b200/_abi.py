@@ -105,7 +105,10 @@ def lib() -> ctypes.CDLL:
         "pk_whir_sumcheck_round_sharded": (c_int, [vp, vp, vp, vp, vp, c_int, u64p, u64p]),
         "pk_prover_create": (c_int, [vp, POINTER(R1CS), POINTER(vp)]),
         "pk_prover_destroy": (None, [vp]),
+        "pk_prover_shapes": (None, [vp, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
         "pk_prove": (c_int, [vp, u64p, POINTER(Rand), POINTER(vp), POINTER(sz)]),
+        "pk_prove_with_transcript": (c_int, [vp, u64p, POINTER(Rand), vp, vp]),
+        "pk_prove_staged_with_transcript": (c_int, [vp, vp, vp]),
         "pk_free": (None, [vp]),
         "pk_prover_timings": (None, [vp, POINTER(c_double)]),
         "pk_np_encode": (c_int, [vp, sz, POINTER(vp), POINTER(sz)]),

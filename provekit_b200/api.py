@@ -398,9 +398,26 @@ class Prover:
         h = c_void_p()
         ctx._chk(ctx.L.pk_prover_create(ctx.h, byref(s), byref(h)))
         self.h = h
+        self.num_witnesses = int(r1cs["num_witnesses"])
+        m, m0, mh = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        ctx.L.pk_prover_shapes(h, byref(m), byref(m0), byref(mh))
+        self.m, self.m0, self.mh = m.value, m0.value, mh.value
+
+    def _witness(self, witness):
+        """the C-ABI reads exactly num_witnesses elements from a bare pointer: refuse anything else here
+        (the reference asserts witness.len() == r1cs.num_witnesses(), provekit/prover/src/whir_r1cs.rs:48-54)"""
+        w = _fe(witness)
+        if len(w) != self.num_witnesses:
+            raise PkError(-1, f"witness holds {len(w)} elements, the R1CS has {self.num_witnesses} witnesses")
+        return w
 
     def _rand(self, rand: dict):
+        want = {"mask_w": 1 << (self.m - 1), "g_w": 1 << self.m, "blind": 4 * self.m0, "mask_h": 1 << (self.mh - 1),
+                "g_h": 1 << self.mh}
         arrs = [_fe(rand[k]) for k in ("mask_w", "g_w", "blind", "mask_h", "g_h")]
+        for (k, n), a in zip(want.items(), arrs):
+            if len(a) != n:
+                raise PkError(-1, f"randomness array {k} holds {len(a)} elements, the scheme needs {n}")
         return _abi.Rand(*[a.ctypes.data for a in arrs]), arrs
 
     def _take(self, out, n) -> bytes:
@@ -410,28 +427,37 @@ class Prover:
 
     def prove(self, witness, rand: dict) -> bytes:
         """Host buffers in, spongefish NARG string (WhirR1CSProof.transcript) out."""
-        w = _fe(witness)
+        w = self._witness(witness)
         rs, _keep = self._rand(rand)
         out, n = c_void_p(), c_size_t()
         self.ctx._chk(self.ctx.L.pk_prove(self.h, _p(w), byref(rs), byref(out), byref(n)))
         return self._take(out, n)
 
+    def prove_with_transcript(self, witness, rand: dict, vtbl, user=None) -> None:
+        """WhirR1CSProver::prove with the caller's Fiat-Shamir transcript: `vtbl` points to a pk_transcript_vtbl
+        (ctypes structure or raw address), `user` is handed back to every callback.  The proof string lives on the
+        caller's side (spongefish `ProverState::narg_string()`)."""
+        w = self._witness(witness)
+        rs, _keep = self._rand(rand)
+        vt = vtbl if isinstance(vtbl, (int, c_void_p)) else ctypes.cast(ctypes.pointer(vtbl), c_void_p)
+        self.ctx._chk(self.ctx.L.pk_prove_with_transcript(self.h, _p(w), byref(rs), vt, user))
+
     def upload_inputs(self, witness, rand: dict):
-        w = _fe(witness)
+        w = self._witness(witness)
         rs, _keep = self._rand(rand)
         self.ctx._chk(self.ctx.L.pk_prover_upload_inputs(self.h, _p(w), byref(rs)))
 
     def prove_seeded(self, witness, seed: bytes) -> bytes:
         """pk_prove with the masks drawn on the device from a 32-byte seed: only the witness crosses PCIe."""
         assert len(seed) == 32
-        w = _fe(witness)
+        w = self._witness(witness)
         out, n = c_void_p(), c_size_t()
         self.ctx._chk(self.ctx.L.pk_prove_seeded(self.h, _p(w), seed, byref(out), byref(n)))
         return self._take(out, n)
 
     def upload_inputs_seeded(self, witness, seed: bytes):
         assert len(seed) == 32
-        w = _fe(witness)
+        w = self._witness(witness)
         self.ctx._chk(self.ctx.L.pk_prover_upload_inputs_seeded(self.h, _p(w), seed))
 
     def prove_staged(self) -> bytes:

@@ -83,6 +83,8 @@ int pk_np_encode(const uint8_t* transcript, size_t len, uint8_t** out, size_t* o
     return PK_OK;
 }
 
+static const size_t NP_MAX_INFLATED = (size_t)2 << 30;  // proofs are a few hundred KB
+
 int pk_np_decode(const uint8_t* file, size_t len, uint8_t** transcript, size_t* transcript_len) {
     if (!file || !transcript || !transcript_len) return PK_ERR_INVALID_ARG;
     // bin.rs:86-99: magic, format, major == 0, minor >= 0
@@ -105,7 +107,15 @@ int pk_np_decode(const uint8_t* file, size_t len, uint8_t** transcript, size_t* 
             break;
         }
         payload.insert(payload.end(), chunk.begin(), chunk.begin() + o.pos);
-        if (r == 0 || (in.pos == in.size && o.pos < o.size)) break;
+        if (payload.size() > NP_MAX_INFLATED) {  // a crafted frame must not exhaust host memory
+            rc = PK_ERR_INVALID_ARG;
+            break;
+        }
+        if (r == 0) break;  // frame complete
+        if (in.pos == in.size && o.pos < o.size) {
+            rc = PK_ERR_INVALID_ARG;  // input exhausted in the middle of a frame: truncated file
+            break;
+        }
     }
     z.freeDStream(ds);
     if (rc != PK_OK) return rc;

@@ -42,6 +42,7 @@ struct ZBuf {
 };
 const uint8_t MAGIC[8] = {0xDC, 0xDF, 'O', 'Z', 'k', 'p', 0x01, 0x00};
 const char FORMAT_NPS[9] = "NrProScm";
+const size_t NPS_MAX_INFLATED = (size_t)8 << 30;  // the reference fixture inflates to ~70 MB
 
 bool zstd_inflate(const uint8_t* src, size_t len, std::vector<uint8_t>& out) {
     static void* h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_LOCAL);  // once per process (thread-safe static init)
@@ -66,7 +67,15 @@ bool zstd_inflate(const uint8_t* src, size_t len, std::vector<uint8_t>& out) {
             break;
         }
         out.insert(out.end(), chunk.begin(), chunk.begin() + o.pos);
-        if (r == 0 || (in.pos == in.size && o.pos < o.size)) break;
+        if (out.size() > NPS_MAX_INFLATED) {  // a crafted frame must not exhaust host memory
+            ok = false;
+            break;
+        }
+        if (r == 0) break;  // frame complete
+        if (in.pos == in.size && o.pos < o.size) {
+            ok = false;  // input exhausted in the middle of a frame: truncated file
+            break;
+        }
     }
     freeDStream(ds);
     return ok;
@@ -133,6 +142,7 @@ int pk_nps_read_r1cs(const uint8_t* file, size_t len, pk_nps** out) {
     const uint8_t* b = raw.data();
     const size_t n = raw.size();
     pk_nps* s = new pk_nps();
+    pk_nps* found = nullptr;
     for (size_t at = 1; at + 48 < n; at++) {
         // cheap reject first: a length varint of 2..5 bytes whose value is 8 + 32c, followed by u64 c
         if (!(b[at] & 0x80)) continue;  // 8 + 32c >= 40 < 128 only for c = 1..3: a scheme has more constants
@@ -179,11 +189,19 @@ int pk_nps_read_r1cs(const uint8_t* file, size_t len, pk_nps** out) {
             m[k]->col = s->col[k].data();
             m[k]->val = s->val[k].data();
         }
-        *out = s;
-        return PK_OK;
+        if (found) {  // a second well-formed candidate: the heuristic is ambiguous on this stream, refuse to guess
+            delete found;
+            delete s;
+            return PK_ERR_INVALID_ARG;
+        }
+        found = s;
+        s = new pk_nps();
+        at = p2 - 1;  // keep scanning behind the matched R1CS
     }
     delete s;
-    return PK_ERR_INVALID_ARG;
+    if (!found) return PK_ERR_INVALID_ARG;
+    *out = found;
+    return PK_OK;
 }
 const pk_r1cs* pk_nps_r1cs(const pk_nps* s) { return s ? &s->r1cs : nullptr; }
 int64_t pk_nps_num_public_inputs(const pk_nps* s) { return s ? s->num_public_inputs : -1; }

@@ -187,6 +187,7 @@ struct pk_prover {
     pk_buf *masked_w = nullptr, *g_w = nullptr, *masked_h = nullptr, *g_h = nullptr;
     std::vector<Fr> blind;
     bool staged = false;
+    ~pk_prover();  // frees every device allocation, also after a partially failed pk_prover_create
 };
 
 namespace {
@@ -221,13 +222,13 @@ struct Commitment {
 
 class Prover {
    public:
-    Prover(pk_prover* p, pkh::ProverState& fs) : P(p), ctx(p->ctx), fs(fs) {}
+    Prover(pk_prover* p, pkh::Transcript& fs) : P(p), ctx(p->ctx), fs(fs) {}
     int run();
 
    private:
     pk_prover* P;
     pk_ctx* ctx;
-    pkh::ProverState& fs;
+    pkh::Transcript& fs;
     double* T() { return P->timings; }
 
     int batch_commit(int m, pk_buf* masked_evals, pk_buf* g_evals, Commitment* cm, bool timed);
@@ -600,6 +601,7 @@ int Prover::run() {
     pk_buf* ws[3] = {*wts[0], *wts[1], *wts[2]};
     PK_TRY(whir_prove(P->cw, &cmw, ws, stmts, 3, nw));
     PK_TRY(pk_ctx_sync(ctx));
+    if (!fs.ok()) return pk::set_err(ctx, PK_ERR_INVALID_ARG, "prove: a transcript callback reported failure");
     T()[8] += now_s() - t_start;
     T()[7] = T()[8] - (T()[0] + T()[1] + T()[2] + T()[3] + T()[4] + T()[5] + T()[6]);
     return PK_OK;
@@ -649,7 +651,7 @@ int upload_csr_arrays(pk_ctx* ctx, const std::vector<uint64_t>& rs, const std::v
 }
 int check_csr(pk_ctx* ctx, const pk_csr& m, uint64_t rows, uint64_t cols, uint64_t n_interned) {
     PK_CHECK(ctx, m.num_rows == rows && m.num_cols == cols, "R1CS matrix shape mismatch");
-    PK_CHECK(ctx, m.nnz == 0 || (m.row_start && m.col && m.val), "R1CS matrix has null arrays");
+    PK_CHECK(ctx, (rows == 0 || m.row_start) && (m.nnz == 0 || (m.col && m.val)), "R1CS matrix has null arrays");
     for (uint64_t r = 0; r < rows; r++) {
         uint64_t s = m.row_start[r], e = r + 1 < rows ? m.row_start[r + 1] : m.nnz;
         PK_CHECK(ctx, s <= e && e <= m.nnz, "R1CS row offsets not monotone");
@@ -681,6 +683,7 @@ int upload_csr(pk_ctx* ctx, const pk_csr& m, DevCsr* rows_out, DevCsr* transpose
     return upload_csr_arrays(ctx, cs, rowidx, val, transposed_out);
 }
 void free_csr(DevCsr& c) {
+    if (!c.row_start && !c.col && !c.val && !c.chunk_start) return;
     cudaFree(c.row_start);
     cudaFree(c.col);
     cudaFree(c.val);
@@ -693,6 +696,22 @@ void free_csr(DevCsr& c) {
 }
 
 }  // namespace
+
+pk_prover::~pk_prover() {
+    if (!ctx) return;
+    PK_BIND(ctx);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_interned);
+    pk_buf_free(ctx, masked_w);
+    pk_buf_free(ctx, g_w);
+    pk_buf_free(ctx, masked_h);
+    pk_buf_free(ctx, g_h);
+    free_csr(A);
+    free_csr(B);
+    free_csr(At);
+    free_csr(Bt);
+    free_csr(Ct);
+}
 
 extern "C" {
 
@@ -725,21 +744,11 @@ int pk_prover_create(pk_ctx* ctx, const pk_r1cs* r1cs, pk_prover** out) {
     *out = p.release();
     return PK_OK;
 }
-void pk_prover_destroy(pk_prover* p) {
-    if (!p) return;
-    PK_BIND(p->ctx);
-    cudaStreamSynchronize(p->ctx->stream);
-    cudaFree(p->d_interned);
-    pk_buf_free(p->ctx, p->masked_w);
-    pk_buf_free(p->ctx, p->g_w);
-    pk_buf_free(p->ctx, p->masked_h);
-    pk_buf_free(p->ctx, p->g_h);
-    free_csr(p->A);
-    free_csr(p->B);
-    free_csr(p->At);
-    free_csr(p->Bt);
-    free_csr(p->Ct);
-    delete p;
+void pk_prover_destroy(pk_prover* p) { delete p; }
+void pk_prover_shapes(const pk_prover* p, int* m, int* m0, int* mh) {
+    if (m) *m = p ? p->m : 0;
+    if (m0) *m0 = p ? p->m0 : 0;
+    if (mh) *mh = p ? p->mh : 0;
 }
 // H2D staging of one proof's inputs: witness (zero-padded) || mask, g, blinding cubics || mask, g
 int pk_prover_upload_inputs(pk_prover* p, const uint64_t* witness, const pk_rand* rnd) {
@@ -830,6 +839,25 @@ int pk_prove_staged(pk_prover* p, uint8_t** out, size_t* out_len) {
     *out = buf;
     *out_len = narg.size();
     return PK_OK;
+}
+int pk_prove_staged_with_transcript(pk_prover* p, const pk_transcript_vtbl* vt, void* user) {
+    if (!p) return PK_ERR_INVALID_ARG;
+    pk_ctx* ctx = p->ctx;
+    PK_BIND(ctx);
+    PK_CHECK(ctx, vt && vt->add_scalars && vt->challenge_scalars && vt->add_bytes && vt->challenge_bytes && vt->hint,
+             "prove_with_transcript: incomplete transcript vtable");
+    PK_CHECK(ctx, p->staged, "prove_staged: call pk_prover_upload_inputs first");
+    double keep1 = p->timings[1];
+    std::memset(p->timings, 0, sizeof p->timings);
+    p->timings[1] = keep1;
+    p->timings[8] = keep1;
+    pkh::CallbackTranscript fs(vt, user);
+    Prover pr(p, fs);
+    return pr.run();
+}
+int pk_prove_with_transcript(pk_prover* p, const uint64_t* witness, const pk_rand* rnd, const pk_transcript_vtbl* vt, void* user) {
+    PK_TRY(pk_prover_upload_inputs(p, witness, rnd));
+    return pk_prove_staged_with_transcript(p, vt, user);
 }
 int pk_prove(pk_prover* p, const uint64_t* witness, const pk_rand* rnd, uint8_t** out, size_t* out_len) {
     PK_TRY(pk_prover_upload_inputs(p, witness, rnd));

@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include "../../../include/pkwhir.h"
 #include "fr_host.h"
 
 namespace pkh {
@@ -38,19 +39,60 @@ class Sponge {
     void permute();
 };
 
-class ProverState {
+// The spongefish ProverState surface the path uses (provekit/prover/src/whir_r1cs.rs:240-242,268-272,335-337;
+// pattern provekit/common/src/whir_r1cs.rs:28-39).  Every operation reports failure through ok().
+class Transcript {
+   public:
+    virtual ~Transcript() {}
+    virtual void add_scalars(const Fr* x, size_t n) = 0;
+    virtual void challenge_scalars(Fr* out, size_t n) = 0;
+    virtual void challenge_bytes(uint8_t* out, size_t n) = 0;
+    virtual void add_bytes(const uint8_t* b, size_t n) = 0;
+    virtual void hint(const std::vector<uint8_t>& payload) = 0;
+    virtual bool ok() const { return true; }
+};
+
+// the in-tree default: Skyscraper duplex sponge + proof string kept here
+class ProverState : public Transcript {
    public:
     explicit ProverState(const std::string& domsep);
-    void add_scalars(const Fr* x, size_t n);
-    void challenge_scalars(Fr* out, size_t n);
-    void challenge_bytes(uint8_t* out, size_t n);
-    void add_bytes(const uint8_t* b, size_t n);
-    void hint(const std::vector<uint8_t>& payload);
+    void add_scalars(const Fr* x, size_t n) override;
+    void challenge_scalars(Fr* out, size_t n) override;
+    void challenge_bytes(uint8_t* out, size_t n) override;
+    void add_bytes(const uint8_t* b, size_t n) override;
+    void hint(const std::vector<uint8_t>& payload) override;
     std::vector<uint8_t>& narg() { return narg_; }
 
    private:
     Sponge sp_;
     std::vector<uint8_t> narg_;
+};
+
+// the host's own ProverState behind pk_transcript_vtbl (include/pkwhir.h): sponge, codecs and the proof string all
+// live on the caller's side
+class CallbackTranscript : public Transcript {
+   public:
+    CallbackTranscript(const pk_transcript_vtbl* vt, void* user) : vt_(vt), user_(user) {}
+    void add_scalars(const Fr* x, size_t n) override { note(vt_->add_scalars(user_, x[0].l, n)); }
+    void challenge_scalars(Fr* out, size_t n) override {
+        std::memset(out, 0, n * sizeof(Fr));
+        note(vt_->challenge_scalars(user_, out[0].l, n));
+    }
+    void challenge_bytes(uint8_t* out, size_t n) override {
+        std::memset(out, 0, n);
+        note(vt_->challenge_bytes(user_, out, n));
+    }
+    void add_bytes(const uint8_t* b, size_t n) override { note(vt_->add_bytes(user_, b, n)); }
+    void hint(const std::vector<uint8_t>& payload) override { note(vt_->hint(user_, payload.data(), payload.size())); }
+    bool ok() const override { return ok_; }
+
+   private:
+    const pk_transcript_vtbl* vt_;
+    void* user_;
+    bool ok_ = true;
+    void note(int rc) {
+        if (rc != 0) ok_ = false;
+    }
 };
 
 // domain-separator builder: "\0" + {A,S,H} + count + label per op

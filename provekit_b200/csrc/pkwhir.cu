@@ -787,6 +787,12 @@ int pk_shard_group_set(pk_ctx* ctx, int rank, int world, void* const* mailboxes)
     for (int i = 0; i < world; i++) ctx->shard.mbox[i] = (uint8_t*)mailboxes[i];
     ctx->shard.rank = rank;
     ctx->shard.world = world;
+    // Stale flags: a mailbox that served an earlier group may still hold a flag equal to a sequence number the new group
+    // will use.  Each rank therefore wipes ITS OWN mailbox here (the caller's barrier between group_set and the first
+    // round orders the wipe before any peer's first store), and the sequence number starts at 0 for every group so that all
+    // ranks of a new group agree on it whatever their history.
+    PK_CUDA(ctx, cudaMemsetAsync(mailboxes[rank], 0, SHARD_MAILBOX_BYTES, ctx->stream));
+    PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->shard_seq = 0;
     return PK_OK;
 }
@@ -808,7 +814,13 @@ static int exchange_and_fetch(pk_ctx* ctx, uint64_t out3[12]) {
     PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     std::memcpy(out3, ctx->h_result, 96);
     std::memcpy(&status, ctx->h_result + 16, 4);
-    if (status != 0) return set_err(ctx, PK_ERR_CUDA, "sharded round %u: a peer did not publish its partial sums in time", ctx->shard_seq);
+    if (status != 0) {
+        // the ranks' sequence numbers are no longer in step: the group stays unusable until pk_shard_group_set resets it
+        uint32_t seq = ctx->shard_seq;
+        ctx->shard = {};
+        ctx->shard_seq = 0;
+        return set_err(ctx, PK_ERR_CUDA, "sharded round %u: a peer did not publish its partial sums in time; group disabled", seq);
+    }
     return PK_OK;
 }
 int pk_zk_sumcheck_round_sharded(pk_ctx* ctx, pk_buf* a, pk_buf* b, pk_buf* c, pk_buf* eq, int log_n, const uint64_t* fold,

@@ -29,3 +29,14 @@ def test_decode_rejects_bad_containers():
     for bad in (b"", good[:19], b"X" + good[1:], good[:8] + b"NrProScm" + good[16:], good[:20] + b"garbage"):
         with pytest.raises(pk.PkError):
             pk.np_decode(bad)
+
+
+def test_decode_rejects_truncated_and_oversized_frames():
+    """a zstd frame cut short must be an error, not a silently shorter payload (the input running out with the decoder
+    still expecting data used to be accepted)"""
+    import pytest
+    t = open(os.path.join(GOLD, "poseidon-1000.transcript.bin"), "rb").read()
+    good = pk.np_encode(t)
+    for cut in (len(good) - 1, len(good) - 100, len(good) // 2, 40):
+        with pytest.raises(pk.PkError):
+            pk.np_decode(good[:cut])

@@ -158,3 +158,18 @@ def test_synthetic_workload_has_the_fixture_sparsity_extremes():
             assert abs(ex[k]["col_max"] - real[k]["col_max"]) <= 16
             assert abs(ex[k]["row_max"] - real[k]["row_max"]) <= (4 if real[k]["long_rows"] else 16)
             assert abs(ex[k]["empty"] - real[k]["empty"]) <= 16
+
+
+def test_truncated_frame_and_ambiguous_scheme_are_errors():
+    """(1) a zstd frame cut short is an error even when the cut falls behind the R1CS; (2) two well-formed R1CS
+    candidates in one stream make the locate-by-shape heuristic ambiguous: refuse instead of returning the first"""
+    r = SyntheticR1CS(100, 80, seed=3, n_interned=40)
+    rng = np.random.default_rng(5)
+    tail = rng.integers(0, 256, size=200_000, dtype=np.uint8).tobytes()  # incompressible: the frame's last blocks
+    good = nps_file(b"\x00" * 10 + postcard_r1cs(r) + tail)
+    check_equal(pk.nps_read_r1cs(good), r)
+    with pytest.raises(pk.PkError):
+        pk.nps_read_r1cs(good[:-1000])
+    r2 = SyntheticR1CS(120, 90, seed=4, n_interned=40)
+    with pytest.raises(pk.PkError):
+        pk.nps_read_r1cs(nps_file(b"\x00" * 10 + postcard_r1cs(r) + b"\x00" * 7 + postcard_r1cs(r2)))
