@@ -34,7 +34,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 from tools import workload as wl  # noqa: E402
 
-REPEATS = 2  # timed repetitions of the K-step region; the best one is reported (disclosed in config.timing)
+REPEATS = 5          # timed repetitions; the MEDIAN is reported (config.timing)
+MIN_REGION_STEPS = 150   # a timed repetition covers ceil(MIN_REGION_STEPS / K) * K proofs (>= 1 s), whatever --steps is
+IN_FLIGHT = 8        # independent proofs in flight per GPU, fixed (not derived from --steps)
 
 WORKLOADS = {
     # configs[1]: poseidon-rounds shapes (fixture poseidon-1000.nps): m = 21, m_0 = 20
@@ -146,6 +148,20 @@ def oracle_structs(r1cs, rnd):
     return cs, rs
 
 
+def host_threads():
+    """cores this process may run on (cgroup / affinity aware)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def median(xs):
+    xs = sorted(xs)
+    n = len(xs)
+    return xs[n // 2] if n % 2 else 0.5 * (xs[n // 2 - 1] + xs[n // 2])
+
+
 def cpu_prove_once(orc, cs, rs, witness):
     out = ctypes.c_void_p()
     t0 = time.perf_counter()
@@ -181,10 +197,12 @@ def run_reference(args):
     import oracle
     oracle.build()
     orc = oracle.lib()
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: set the OpenMP team size explicitly, report what is in force
+    cores = host_threads()
+    omp_threads = int(orc.orc_set_threads(cores))
     r1cs = wl.synth_r1cs(**WORKLOADS[args.workload], seed=1)
     rnd = wl.randomness(r1cs)
     cs, rs = oracle_structs(r1cs, rnd)
-    cores = os.cpu_count()
     for _ in range(min(args.warmup, 1)):
         cpu_prove_once(orc, cs, rs, r1cs["witness"])
     t = [cpu_prove_once(orc, cs, rs, r1cs["witness"])[0] for _ in range(args.steps)]
@@ -192,7 +210,8 @@ def run_reference(args):
     line = base_line(args, args.workload, r1cs)
     v = args.steps / total
     line.update({"impl": "reference", "value": v, "ms_per_step": 1e3 * total / args.steps, "gpu_launches": 0,
-                 "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": cores, "kind": "port",
+                 "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": omp_threads, "omp_threads": omp_threads,
+                                  "host_cores": cores, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"), "kind": "port",
                                   "sample": f"{args.steps} full proof(s) of the same workload; C restatement of the reference "
                                             "algorithms (the Rust reference is aarch64-only and has no toolchain here)"},
                  "e2e": {"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
@@ -209,8 +228,7 @@ def main():
     ap.add_argument("--workload", default="poseidon-1000", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--in-flight", type=int, default=0,
-                    help="independent proofs in flight per GPU, 0 = auto (own ctx/stream/host thread each): the host<->device "
-                         "round trips of one proof (~120 challenges) are hidden behind the kernels of the other")
+                    help=f"independent proofs in flight per GPU (own ctx/stream/host thread each), 0 = {IN_FLIGHT}")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 3:
@@ -254,12 +272,10 @@ def main():
         rnd_p[k], t_ = pin(v)
         keep.append(t_)
 
-    # default: up to 8 proofs in flight, chosen so that the K timed proofs split evenly over the workers (an uneven split
-    # leaves the GPU half empty while the last worker finishes)
-    n_fl = args.in_flight
-    if n_fl <= 0:
-        even = [f for f in range(8, 3, -1) if args.steps % f == 0]
-        n_fl = even[0] if even else min(8, max(1, args.steps))
+    # proofs in flight per GPU: fixed (each has its own ctx / stream / host thread); the K..K_region proofs of a timed region
+    # are handed out dynamically, so the count need not divide K
+    n_fl = args.in_flight if args.in_flight > 0 else IN_FLIGHT
+    region = max(args.steps, -(-MIN_REGION_STEPS // args.steps) * args.steps)  # proofs per timed repetition
     ctxs = [pk.Context(local_rank) for _ in range(n_fl)]
     provers = [pk.Prover(c, r1cs) for c in ctxs]
     streams = [torch.cuda.ExternalStream(c.stream) for c in ctxs]
@@ -275,13 +291,18 @@ def main():
     d2h = len(proof) + 32 * (3 * (m0 + 4 * 12) + 64)  # transcript + per-round result scalars (approx.)
 
     def run_concurrent(fn, steps):
-        """`steps` proofs spread over the in-flight workers; device time from an event on stream 0 before the
+        """`steps` proofs handed out dynamically to the in-flight workers; device time from an event on stream 0 before the
         first launch to an event after every stream has drained (stream 0 waits on the others)."""
-        per = [steps // n_fl + (1 if i < steps % n_fl else 0) for i in range(n_fl)]
         results = [None] * n_fl
+        lock, nxt = threading.Lock(), [0]
 
         def work(i):
-            for _ in range(per[i]):
+            while True:
+                with lock:
+                    k = nxt[0]
+                    nxt[0] += 1
+                if k >= steps:
+                    return
                 results[i] = fn(provers[i])
 
         for c in ctxs:
@@ -303,9 +324,9 @@ def main():
         for c in ctxs:
             c.sync()
         wall = (time.perf_counter() - t0) * 1e3
-        return max(e0.elapsed_time(e1), 0.0), wall, results[0]
+        return max(e0.elapsed_time(e1), 0.0), wall, next(r for r in results if r is not None)
 
-    # ---- device-resident arm: inputs staged once per worker, K proofs from HBM ----
+    # ---- device-resident arm: inputs staged once per worker, proofs from HBM ----
     for p_ in provers:
         p_.upload_inputs_seeded(witness, seed)
         p_.prove_staged()
@@ -329,23 +350,17 @@ def main():
     single_ms = e0.elapsed_time(e1)
     launches = ctx.launches - launches0
     stage_t = prover.timings()
-    # (b) the measured configuration: n_fl proofs in flight
+    # (b) the measured configuration: n_fl proofs in flight, REPEATS repetitions of `region` proofs, median
     barrier()
-    if n_fl > 1:
-        # untimed: thread start-up, first concurrent launches, and the stream-ordered memory pool growing to the footprint
-        # of n_fl overlapping proofs (a pool that still grows inside the timed region costs device-wide syncs)
-        run_concurrent(lambda p_: p_.prove_staged(), 3 * n_fl)
-        barrier()
-        # best of REPEATS timed repetitions of exactly K steps (host-side noise on shared boxes); every repetition is
-        # bracketed by barriers and counted as its slowest rank
-        reps = []
-        for _ in range(REPEATS):
-            barrier()
-            reps.append(max_over_ranks(run_concurrent(lambda p_: p_.prove_staged(), args.steps)[0]))
-        dev_ms, dev_reps = min(reps), [round(x, 3) for x in reps]
-    else:
-        dev_ms = max_over_ranks(single_ms)
-        dev_reps = [round(dev_ms, 3)]
+    # untimed: thread start-up, first concurrent launches, and the stream-ordered memory pool growing to the footprint
+    # of n_fl overlapping proofs (a pool that still grows inside the timed region costs device-wide syncs)
+    run_concurrent(lambda p_: p_.prove_staged(), 3 * n_fl)
+    barrier()
+    reps = []
+    for _ in range(REPEATS):
+        barrier()  # every repetition is bracketed by barriers and counted as its slowest rank
+        reps.append(max_over_ranks(run_concurrent(lambda p_: p_.prove_staged(), region)[0]))
+    dev_ms, dev_reps = median(reps), [round(x, 3) for x in reps]
     barrier()
     single_ms = max_over_ranks(single_ms)
 
@@ -355,17 +370,19 @@ def main():
     reps = []
     for _ in range(REPEATS):
         barrier()
-        ms2, wall2, proof = run_concurrent(lambda p_: p_.prove_seeded(witness, seed), args.steps)
+        ms2, wall2, proof = run_concurrent(lambda p_: p_.prove_seeded(witness, seed), region)
         reps.append((max_over_ranks(max(ms2, wall2)), ms2, wall2))
     barrier()
-    e2e_ms, e2e_dev, e2e_wall = min(reps)
+    e2e_ms = median([r[0] for r in reps])
+    e2e_dev, e2e_wall = median([r[1] for r in reps]), median([r[2] for r in reps])
     e2e_detail = {"device_ms": e2e_dev, "wall_ms": e2e_wall, "repetitions_ms": [round(r[0], 3) for r in reps],
                   "host_stage_s_last_proof": dict(zip(
         ["commit", "h2d", "zk_sumcheck", "whir_sumcheck", "pow", "open", "spmv_weights", "other", "total"], [round(x, 5) for x in prover.timings()]))}
-    # the same with the masks as host arrays (the explicit-mask entry point the parity tests use)
+    # the same with the masks as host arrays (the reference's API semantics: the host owns the randomness), one repetition
     run_concurrent(lambda p_: p_.prove(witness, rnd_p), n_fl)
     barrier()
-    hm_ms, hm_wall, _ = run_concurrent(lambda p_: p_.prove(witness, rnd_p), args.steps)
+    hm_steps = max(args.steps, 4 * n_fl)
+    hm_ms, hm_wall, _ = run_concurrent(lambda p_: p_.prove(witness, rnd_p), hm_steps)
     barrier()
     hm_ms = max_over_ranks(max(hm_ms, hm_wall))
     clocks = sampler.finish() if sampler else None
@@ -373,18 +390,20 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak()
         line = base_line(args, args.workload, r1cs)
-        value = aggregate_throughput(args.steps, world, dev_ms)
+        value = aggregate_throughput(region, world, dev_ms)
         line["config"]["in_flight_proofs_per_gpu"] = n_fl
         line["config"]["host_wait"] = "blocking sync" if blocking else "spin (CUDA default)"
         line["config"]["host_cores"] = os.cpu_count()
-        line["config"]["timing"] = (f"value and e2e: best of {REPEATS} timed repetitions of exactly K = {args.steps} steps each "
-                                    "(CUDA events; e2e additionally bounded below by host wall clock), max over ranks")
-        line.update({"value": value, "ms_per_step": dev_ms / args.steps, "ms_per_step_one_in_flight": single_ms / args.steps,
+        line["config"]["timing"] = (f"value and e2e: MEDIAN of {REPEATS} timed repetitions of {region} proofs each (a multiple of "
+                                    f"K = {args.steps}, at least {MIN_REGION_STEPS}: >= 1 s per repetition), {n_fl} proofs in flight handed "
+                                    "out dynamically; CUDA events (e2e additionally bounded below by host wall clock), max over ranks")
+        line["timed_steps_per_repetition"] = region
+        line.update({"value": value, "ms_per_step": dev_ms / region, "ms_per_step_one_in_flight": single_ms / args.steps,
                      "gpu_launches": int(launches), "clocks": clocks,
-                     "e2e": {"value": aggregate_throughput(args.steps, world, e2e_ms), "unit": "proofs/s", "h2d_bytes_per_step": int(h2d),
+                     "e2e": {"value": aggregate_throughput(region, world, e2e_ms), "unit": "proofs/s", "h2d_bytes_per_step": int(h2d),
                              "d2h_bytes_per_step": int(d2h)},
                      "value_repetitions_ms": dev_reps, "e2e_detail": e2e_detail,
-                     "e2e_host_masks": {"value": aggregate_throughput(args.steps, world, hm_ms), "unit": "proofs/s",
+                     "e2e_host_masks": {"value": aggregate_throughput(hm_steps, world, hm_ms), "unit": "proofs/s",
                                         "h2d_bytes_per_step": int(h2d_host_masks), "d2h_bytes_per_step": int(d2h)}})
         # roofline of the dominant kernel: Merkle leaf hashing of the witness commitment (L = 2^(m-3) leaves of 32)
         L = 1 << (m + 1 - 4)
@@ -409,9 +428,15 @@ def main():
         ntt_ms = ms_cls[0] / args.steps
         if ntt_ms > 0:
             nb = wl.rs_encode_bytes(m, mh)
-            line["roofline_ntt"] = {"kernel": "k_ntt_pass (RS-encode, all commitments of one proof)", "bound": "hbm",
+            ntt_traffic = None
+            try:
+                ntt_traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["rs_encode"]["dram_bytes_per_proof"]
+            except Exception:
+                pass
+            line["roofline_ntt"] = {"kernel": "RS-encode NTT passes, all commitments of one proof", "bound": "hbm",
                                     "achieved": nb / (ntt_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                                    "frac": nb / (ntt_ms / 1e3) / 1e9 / peak, "traffic": None}
+                                    "frac": nb / (ntt_ms / 1e3) / 1e9 / peak, "traffic": ntt_traffic, "algorithmic_bytes": nb,
+                                    "ms_per_proof": ntt_ms}
         line["host_stage_s_last_proof"] = dict(zip(["commit", "h2d", "zk_sumcheck", "whir_sumcheck", "pow", "open", "spmv_weights",
                                                     "other", "total"], [round(x, 5) for x in stage_t]))
         if world == 1 and not args.no_cpu_baseline:
@@ -423,8 +448,9 @@ def main():
                      (("mask_w", 1 << (m - 1)), ("g_w", 1 << m), ("blind", 4 * m0), ("mask_h", 1 << (mh - 1)), ("g_h", 1 << mh))}
             orc.orc_rng_masks(seed, m, m0, mh, *[a.ctypes.data_as(ctypes.c_void_p) for a in masks.values()])
             cs, rs = oracle_structs(r1cs, masks)
+            omp_threads = int(orc.orc_set_threads(host_threads()))
             dt, cpu_proof = cpu_prove_once(orc, cs, rs, r1cs["witness"])
-            line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "proofs/s", "cores": os.cpu_count(), "kind": "port",
+            line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "proofs/s", "cores": omp_threads, "omp_threads": omp_threads, "kind": "port",
                                     "sample": "1 full proof of the same workload (same witness, masks); C restatement of the "
                                               "reference algorithms with OpenMP",
                                     "proof_matches_gpu": bool(cpu_proof == proof)}

@@ -228,6 +228,11 @@ void pk_prover_destroy(pk_prover *p);
  * pk_rand arrays 2^(m-1), 2^m, 4*m_0, 2^(mh-1), 2^mh elements: the library reads exactly that many and cannot check a
  * bare pointer, so callers size their buffers from these numbers */
 void pk_prover_shapes(const pk_prover *p, int *m, int *m0, int *mh);
+/* seam: `impl Mul<&[FieldElement]> for HydratedSparseMatrix` / `impl Mul<HydratedSparseMatrix> for &[FieldElement]`
+ * (provekit/common/src/sparse_matrix.rs:148-184) on the uploaded R1CS; which = 0 A, 1 B, 2 C.  transposed = 0: out = M x
+ * (x: num_witnesses -> out: num_constraints; not for C, the path forms c = a o b instead); transposed = 1: out = x^T M
+ * (x: num_constraints -> out: num_witnesses), the rows of calculate_external_row_of_r1cs_matrices (sumcheck.rs:207-218). */
+int pk_prover_matvec(pk_prover *p, int which, int transposed, const pk_buf *x, pk_buf *out);
 /* returns the spongefish NARG string (= WhirR1CSProof.transcript); *out is malloc'd, free with pk_free */
 int pk_prove(pk_prover *p, const uint64_t *witness, const pk_rand *rnd, uint8_t **out, size_t *out_len);
 /* the two halves of pk_prove, exposed so that a caller can keep one proof's inputs resident in HBM:

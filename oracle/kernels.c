@@ -8,6 +8,21 @@
 
 fr_t orc_compress_fr(fr_t l, fr_t r); /* skyscraper.c */
 
+/* OpenMP team size of every parallel region of the oracle (bench.py --impl reference: torchrun exports OMP_NUM_THREADS=1,
+ * which silently made the CPU arm single-threaded).  n <= 0 leaves the setting alone.  Returns the team size in force. */
+#ifdef _OPENMP
+#include <omp.h>
+int orc_set_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+}
+#else
+int orc_set_threads(int n) {
+    (void)n;
+    return 1;
+}
+#endif
+
 static inline fr_t ld(const uint64_t *p, size_t i) {
     fr_t x;
     memcpy(x.l, p + 4 * i, 32);

@@ -26,6 +26,9 @@
 extern "C" {
 #endif
 
+/* OpenMP team size of the oracle's parallel loops; n <= 0 only queries.  Returns the size in force. */
+int orc_set_threads(int n);
+
 /* ---- Skyscraper (canonical LE integers) ---- */
 void orc_sky_permute(const uint64_t l[4], const uint64_t r[4], uint64_t lo[4], uint64_t ro[4]);
 void orc_sky_compress(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]);
@@ -81,6 +84,8 @@ typedef struct {
     const uint64_t *interned; /* Montgomery */
     orc_csr a, b, c;
 } orc_r1cs;
+/* provekit/common/src/sparse_matrix.rs:148-165 (M x, transposed == 0) and :168-184 (x^T M) */
+void orc_r1cs_matvec(const orc_csr *m, const uint64_t *interned, const uint64_t *x, uint64_t *out, int transposed);
 /* Randomness the reference draws from thread_rng is an input here. */
 typedef struct {
     const uint64_t *mask_w;   /* 2^(m-1) */

@@ -503,6 +503,15 @@ static void vec_mul_csr(const orc_csr *m, const uint64_t *interned, const fr_t *
         }
     }
 }
+/* exported for the kernel-level SpMV parity tests: out = M x (transposed == 0) or out = x^T M (out zeroed here) */
+void orc_r1cs_matvec(const orc_csr *m, const uint64_t *interned, const uint64_t *x, uint64_t *out, int transposed) {
+    if (transposed) {
+        memset(out, 0, m->num_cols * sizeof(fr_t));
+        vec_mul_csr(m, interned, (const fr_t *)x, (fr_t *)out);
+    } else {
+        csr_mul_vec(m, interned, (const fr_t *)x, (fr_t *)out);
+    }
+}
 /* compute_blinding_coefficients_for_round, whir_r1cs.rs:103-171 */
 static void blinding_coeffs_for_round(const fr_t *g /* n x 4 */, int n, int compute_for, const fr_t *alphas, fr_t out[4]) {
     int all_fixed = 0;

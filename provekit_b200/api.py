@@ -399,9 +399,17 @@ class Prover:
         ctx._chk(ctx.L.pk_prover_create(ctx.h, byref(s), byref(h)))
         self.h = h
         self.num_witnesses = int(r1cs["num_witnesses"])
+        self.num_constraints = int(r1cs["num_constraints"])
         m, m0, mh = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         ctx.L.pk_prover_shapes(h, byref(m), byref(m0), byref(mh))
         self.m, self.m0, self.mh = m.value, m0.value, mh.value
+
+    def matvec(self, which: int, x: "Buffer", transposed: bool = False) -> "Buffer":
+        """HydratedSparseMatrix * vector (sparse_matrix.rs:148-165) or vector * matrix (:168-184); which = 0 A, 1 B, 2 C"""
+        n_out = self.num_witnesses if transposed else self.num_constraints
+        out = Buffer(self.ctx, n_out)
+        self.ctx._chk(self.ctx.L.pk_prover_matvec(self.h, which, 1 if transposed else 0, x.h, out.h))
+        return out
 
     def _witness(self, witness):
         """the C-ABI reads exactly num_witnesses elements from a bare pointer: refuse anything else here

@@ -745,6 +745,21 @@ int pk_prover_create(pk_ctx* ctx, const pk_r1cs* r1cs, pk_prover** out) {
     return PK_OK;
 }
 void pk_prover_destroy(pk_prover* p) { delete p; }
+// seam: `impl Mul<&[FieldElement]> for HydratedSparseMatrix` and its transposed twin (provekit/common/src/sparse_matrix.rs:
+// 148-184) on the device-resident R1CS: out = M x (x: num_witnesses, out: num_constraints) or out = x^T M (x:
+// num_constraints, out: num_witnesses).  C x is not available: the prover never forms it (c = a o b, sumcheck.rs:181-193).
+int pk_prover_matvec(pk_prover* p, int which, int transposed, const pk_buf* x, pk_buf* out) {
+    if (!p) return PK_ERR_INVALID_ARG;
+    pk_ctx* ctx = p->ctx;
+    PK_BIND(ctx);
+    PK_CHECK(ctx, x && out && which >= 0 && which <= 2, "matvec: bad arguments");
+    PK_CHECK(ctx, transposed || which < 2, "matvec: C x is not formed on this path (c = a o b)");
+    const DevCsr* M = transposed ? (which == 0 ? &p->At : which == 1 ? &p->Bt : &p->Ct) : (which == 0 ? &p->A : &p->B);
+    const size_t n_in = transposed ? p->num_constraints : p->num_witnesses, n_out = transposed ? p->num_witnesses : p->num_constraints;
+    PK_CHECK(ctx, x->n >= n_in && out->n >= n_out, "matvec: buffer too small");
+    PK_TRY(pk_buf_zero(ctx, out, 0, n_out));
+    return spmv(ctx, *M, p->d_interned, x->d, out->d, n_out);
+}
 void pk_prover_shapes(const pk_prover* p, int* m, int* m0, int* mh) {
     if (m) *m = p ? p->m : 0;
     if (m0) *m0 = p ? p->m0 : 0;

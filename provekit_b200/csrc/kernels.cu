@@ -425,43 +425,103 @@ int launch_rs_encode(cudaStream_t st, const void* coeffs, int log_n, int log_inv
 // src/skyscraper/whir.rs:30-48), inner nodes = compress(left, right) (:53-74).  Digests are kept
 // CANONICAL on device (that is the form compress consumes and the transcript carries).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_merkle_leaves(const fr* __restrict__ leaves, size_t L, int w, fr* nodes) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= L) return;
-    const fr* leaf = leaves + i * w;
-    fr d = fr_from_mont(fr_load_nc(&leaf[0]));
-    for (int k = 1; k < w; k++) d = sky_compress(d, fr_from_mont(fr_load_nc(&leaf[k])));
-    fr_store(&nodes[L + i], d);
+// One launch hashes the leaves AND the levels above them that fit in the block: a block of MERKLE_LEAF_BLOCK threads owns
+// that many consecutive leaves, i.e. one aligned sub-tree; after the leaf fold the digests go through shared memory level by
+// level (every inner node is also stored: pk_commit_open needs the whole tree).  The upper part of the tree is then at most
+// two more launches of k_merkle_reduce instead of one launch per level (each level cost a full launch + one compress
+// latency, ~11 us, with the GPU almost empty).
+constexpr int MERKLE_LEAF_BLOCK = 128;
+constexpr int MERKLE_TOP_MAX_IN = 2048;  // inputs one block of 1024 threads reduces to the root
+// CANON: the leaf elements are already canonical integers (the commit path's RS-encode emits them that way, see
+// NttPass::canonical); otherwise they are Montgomery-form field elements (provekit/common/src/skyscraper/whir.rs:21-24
+// converts each one with into_bigint)
+template <bool CANON>
+__global__ void __launch_bounds__(MERKLE_LEAF_BLOCK) k_merkle_leaves(const fr* __restrict__ leaves, size_t L, int w, fr* nodes) {
+    __shared__ fr sd[MERKLE_LEAF_BLOCK];
+    const int tid = threadIdx.x;
+    const size_t i = (size_t)blockIdx.x * MERKLE_LEAF_BLOCK + tid;
+    if (i < L) {
+        const fr* leaf = leaves + i * w;
+        fr d = fr_load_nc(&leaf[0]);
+        if (!CANON) d = fr_from_mont(d);
+        for (int k = 1; k < w; k++) {
+            fr x = fr_load_nc(&leaf[k]);
+            d = sky_compress(d, CANON ? x : fr_from_mont(x));
+        }
+        fr_store(&nodes[L + i], d);
+        sd[tid] = d;
+    }
+    // levels inside the block's sub-tree (L is a power of two: blocks are full unless L < MERKLE_LEAF_BLOCK)
+    const int nb = L < (size_t)MERKLE_LEAF_BLOCK ? (int)L : MERKLE_LEAF_BLOCK;
+    size_t lvl = L, off = (size_t)blockIdx.x * MERKLE_LEAF_BLOCK;
+    for (int n = nb >> 1; n >= 1; n >>= 1) {
+        __syncthreads();
+        fr a, b;
+        const bool act = tid < n;
+        if (act) {
+            a = sd[2 * tid];
+            b = sd[2 * tid + 1];
+        }
+        __syncthreads();
+        lvl >>= 1;
+        off >>= 1;
+        if (act) {
+            fr h = sky_compress(a, b);
+            sd[tid] = h;
+            fr_store(&nodes[lvl + off + tid], h);
+        }
+    }
 }
-__global__ void __launch_bounds__(128) k_merkle_level(fr* nodes, size_t lvl) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= lvl) return;
-    size_t node = lvl + i;
-    fr_store(&nodes[node], sky_compress(fr_load(&nodes[2 * node]), fr_load(&nodes[2 * node + 1])));
-}
-// all levels from `top` (<= 256 nodes) down to the root in one block
-__global__ void __launch_bounds__(256) k_merkle_top(fr* nodes, int top) {
-    for (int lvl = top; lvl >= 1; lvl >>= 1) {
-        if ((int)threadIdx.x < lvl) {
-            int node = lvl + threadIdx.x;
-            fr_store(&nodes[node], sky_compress(fr_load(&nodes[2 * node]), fr_load(&nodes[2 * node + 1])));
+// n_in nodes of one tree level (heap positions [n_in, 2 n_in)) -> every block reduces `per_block` (= 2 * blockDim.x) of them
+// through log2(per_block) levels to one node, storing all inner nodes
+__global__ void __launch_bounds__(1024) k_merkle_reduce(fr* nodes, size_t n_in, int per_block) {
+    extern __shared__ uint4 smem_raw[];
+    fr* sd = reinterpret_cast<fr*>(smem_raw);
+    const int tid = threadIdx.x;
+    size_t lvl = n_in, off = (size_t)blockIdx.x * per_block;
+    for (int n = per_block >> 1; n >= 1; n >>= 1) {
+        fr a, b;
+        const bool act = tid < n;
+        if (act) {
+            if (n == per_block >> 1) {  // first level: children come from global memory
+                a = fr_load(&nodes[lvl + off + 2 * tid]);
+                b = fr_load(&nodes[lvl + off + 2 * tid + 1]);
+            } else {
+                a = sd[2 * tid];
+                b = sd[2 * tid + 1];
+            }
+        }
+        __syncthreads();
+        lvl >>= 1;
+        off >>= 1;
+        if (act) {
+            fr h = sky_compress(a, b);
+            sd[tid] = h;
+            fr_store(&nodes[lvl + off + tid], h);
         }
         __syncthreads();
     }
 }
-int launch_merkle_leaves(cudaStream_t st, const void* leaves, size_t L, size_t w, void* nodes) {
-    k_merkle_leaves<<<(unsigned)((L + 127) / 128), 128, 0, st>>>((const fr*)leaves, L, (int)w, (fr*)nodes);
+int launch_merkle_leaves(cudaStream_t st, const void* leaves, size_t L, size_t w, void* nodes, bool canonical) {
+    const unsigned grid = (unsigned)((L + MERKLE_LEAF_BLOCK - 1) / MERKLE_LEAF_BLOCK);
+    if (canonical)
+        k_merkle_leaves<true><<<grid, MERKLE_LEAF_BLOCK, 0, st>>>((const fr*)leaves, L, (int)w, (fr*)nodes);
+    else
+        k_merkle_leaves<false><<<grid, MERKLE_LEAF_BLOCK, 0, st>>>((const fr*)leaves, L, (int)w, (fr*)nodes);
     return 1;
 }
+// the levels above what the leaf kernel already produced (it leaves L / MERKLE_LEAF_BLOCK sub-tree roots)
 int launch_merkle_upper(cudaStream_t st, size_t L, void* nodes) {
     int launches = 0;
-    size_t lvl = L / 2;
-    for (; lvl > 256; lvl >>= 1) {
-        k_merkle_level<<<(unsigned)((lvl + 127) / 128), 128, 0, st>>>((fr*)nodes, lvl);
+    size_t n = L / MERKLE_LEAF_BLOCK;  // nodes of the highest level hashed so far (0 or 1: nothing left)
+    while (n > (size_t)MERKLE_TOP_MAX_IN) {
+        k_merkle_reduce<<<(unsigned)(n / 256), 128, 128 * sizeof(fr), st>>>((fr*)nodes, n, 256);
+        n /= 256;
         launches++;
     }
-    if (lvl >= 1) {
-        k_merkle_top<<<1, 256, 0, st>>>((fr*)nodes, (int)lvl);
+    if (n >= 2) {
+        const int threads = (int)(n / 2) < 32 ? 32 : (int)(n / 2);
+        k_merkle_reduce<<<1, threads, (n / 2) * sizeof(fr), st>>>((fr*)nodes, n, (int)n);
         launches++;
     }
     return launches;

@@ -44,7 +44,8 @@ int launch_rs_encode_cols(cudaStream_t st, const void* coeffs, int log_n, int lo
                           const void* table, int table_log_m);
 
 // K2 Merkle: leaves Montgomery, nodes canonical heap order
-int launch_merkle_leaves(cudaStream_t st, const void* leaves, size_t L, size_t w, void* nodes);
+// canonical: the leaf elements are canonical integers already (no Montgomery conversion before hashing)
+int launch_merkle_leaves(cudaStream_t st, const void* leaves, size_t L, size_t w, void* nodes, bool canonical);
 int launch_merkle_upper(cudaStream_t st, size_t L, void* nodes);
 
 // tensor-product tables of K points with nv_hi + nv_lo variables each (point k at points[k*pt_stride ..]):

@@ -437,7 +437,7 @@ int pk_merkle_build(pk_ctx* ctx, const pk_buf* leaves, size_t L, size_t w, pk_bu
     PK_CHECK(ctx, leaves->n >= L * w && nodes->n >= 2 * L, "merkle_build: buffer too small");
     {
         ProfScope ps(ctx, PROF_MERKLE_LEAVES);
-        ctx->launches += launch_merkle_leaves(ctx->stream, leaves->d, L, w, nodes->d);
+        ctx->launches += launch_merkle_leaves(ctx->stream, leaves->d, L, w, nodes->d, false);
     }
     {
         ProfScope ps(ctx, PROF_MERKLE_UPPER);
@@ -470,7 +470,7 @@ int pk_commit_batch(pk_ctx* ctx, const pk_buf* const* coeffs, int batch, int log
     }
     {
         ProfScope ps(ctx, PROF_MERKLE_LEAVES);
-        ctx->launches += launch_merkle_leaves(ctx->stream, c->leaves, c->L, c->w, c->nodes);
+        ctx->launches += launch_merkle_leaves(ctx->stream, c->leaves, c->L, c->w, c->nodes, false);
     }
     {
         ProfScope ps(ctx, PROF_MERKLE_UPPER);
