@@ -30,6 +30,8 @@ import time
 
 import numpy as np
 
+# one hardware work queue per in-flight proof stream (default 8 would alias them with torch's streams); before CUDA init
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 from tools import workload as wl  # noqa: E402

@@ -425,11 +425,11 @@ int launch_rs_encode(cudaStream_t st, const void* coeffs, int log_n, int log_inv
 // src/skyscraper/whir.rs:30-48), inner nodes = compress(left, right) (:53-74).  Digests are kept
 // CANONICAL on device (that is the form compress consumes and the transcript carries).
 // ------------------------------------------------------------------------------------------------
-// One launch hashes the leaves AND the levels above them that fit in the block: a block of MERKLE_LEAF_BLOCK threads owns
-// that many consecutive leaves, i.e. one aligned sub-tree; after the leaf fold the digests go through shared memory level by
-// level (every inner node is also stored: pk_commit_open needs the whole tree).  The upper part of the tree is then at most
-// two more launches of k_merkle_reduce instead of one launch per level (each level cost a full launch + one compress
-// latency, ~11 us, with the GPU almost empty).
+// Launch structure: one leaf kernel (pure leaf folds: the ALU-bound bulk, kept free of any block-level tail), then the
+// inner levels in at most two launches of k_merkle_reduce, each block taking an aligned sub-tree through 8-10 levels in
+// shared memory (every inner node is also stored: pk_commit_open needs the whole tree).  One launch per level, as before,
+// cost a launch gap + one compress latency (~11 us) per level with the GPU almost empty; hashing the block's levels inside
+// the leaf kernel was measured slower (the divergent tail holds the block's registers: 2.16 vs 1.98 ms on 2^18 x 32).
 constexpr int MERKLE_LEAF_BLOCK = 128;
 constexpr int MERKLE_TOP_MAX_IN = 2048;  // inputs one block of 1024 threads reduces to the root
 // CANON: the leaf elements are already canonical integers (the commit path's RS-encode emits them that way, see
@@ -437,40 +437,16 @@ constexpr int MERKLE_TOP_MAX_IN = 2048;  // inputs one block of 1024 threads red
 // converts each one with into_bigint)
 template <bool CANON>
 __global__ void __launch_bounds__(MERKLE_LEAF_BLOCK) k_merkle_leaves(const fr* __restrict__ leaves, size_t L, int w, fr* nodes) {
-    __shared__ fr sd[MERKLE_LEAF_BLOCK];
-    const int tid = threadIdx.x;
-    const size_t i = (size_t)blockIdx.x * MERKLE_LEAF_BLOCK + tid;
-    if (i < L) {
-        const fr* leaf = leaves + i * w;
-        fr d = fr_load_nc(&leaf[0]);
-        if (!CANON) d = fr_from_mont(d);
-        for (int k = 1; k < w; k++) {
-            fr x = fr_load_nc(&leaf[k]);
-            d = sky_compress(d, CANON ? x : fr_from_mont(x));
-        }
-        fr_store(&nodes[L + i], d);
-        sd[tid] = d;
+    const size_t i = (size_t)blockIdx.x * MERKLE_LEAF_BLOCK + threadIdx.x;
+    if (i >= L) return;
+    const fr* leaf = leaves + i * w;
+    fr d = fr_load_nc(&leaf[0]);
+    if (!CANON) d = fr_from_mont(d);
+    for (int k = 1; k < w; k++) {
+        fr x = fr_load_nc(&leaf[k]);
+        d = sky_compress(d, CANON ? x : fr_from_mont(x));
     }
-    // levels inside the block's sub-tree (L is a power of two: blocks are full unless L < MERKLE_LEAF_BLOCK)
-    const int nb = L < (size_t)MERKLE_LEAF_BLOCK ? (int)L : MERKLE_LEAF_BLOCK;
-    size_t lvl = L, off = (size_t)blockIdx.x * MERKLE_LEAF_BLOCK;
-    for (int n = nb >> 1; n >= 1; n >>= 1) {
-        __syncthreads();
-        fr a, b;
-        const bool act = tid < n;
-        if (act) {
-            a = sd[2 * tid];
-            b = sd[2 * tid + 1];
-        }
-        __syncthreads();
-        lvl >>= 1;
-        off >>= 1;
-        if (act) {
-            fr h = sky_compress(a, b);
-            sd[tid] = h;
-            fr_store(&nodes[lvl + off + tid], h);
-        }
-    }
+    fr_store(&nodes[L + i], d);
 }
 // n_in nodes of one tree level (heap positions [n_in, 2 n_in)) -> every block reduces `per_block` (= 2 * blockDim.x) of them
 // through log2(per_block) levels to one node, storing all inner nodes
@@ -510,13 +486,14 @@ int launch_merkle_leaves(cudaStream_t st, const void* leaves, size_t L, size_t w
         k_merkle_leaves<false><<<grid, MERKLE_LEAF_BLOCK, 0, st>>>((const fr*)leaves, L, (int)w, (fr*)nodes);
     return 1;
 }
-// the levels above what the leaf kernel already produced (it leaves L / MERKLE_LEAF_BLOCK sub-tree roots)
+// all inner levels: L leaf digests at heap positions [L, 2L) -> root at nodes[1]
 int launch_merkle_upper(cudaStream_t st, size_t L, void* nodes) {
     int launches = 0;
-    size_t n = L / MERKLE_LEAF_BLOCK;  // nodes of the highest level hashed so far (0 or 1: nothing left)
+    size_t n = L;
     while (n > (size_t)MERKLE_TOP_MAX_IN) {
-        k_merkle_reduce<<<(unsigned)(n / 256), 128, 128 * sizeof(fr), st>>>((fr*)nodes, n, 256);
-        n /= 256;
+        const int per_block = n > ((size_t)1 << 19) ? 1024 : 256;  // keeps any tree of up to 2^21 leaves at three launches
+        k_merkle_reduce<<<(unsigned)(n / per_block), per_block / 2, (per_block / 2) * sizeof(fr), st>>>((fr*)nodes, n, per_block);
+        n /= per_block;
         launches++;
     }
     if (n >= 2) {
