@@ -233,6 +233,14 @@ void pk_prover_shapes(const pk_prover *p, int *m, int *m0, int *mh);
  * (x: num_witnesses -> out: num_constraints; not for C, the path forms c = a o b instead); transposed = 1: out = x^T M
  * (x: num_constraints -> out: num_witnesses), the rows of calculate_external_row_of_r1cs_matrices (sumcheck.rs:207-218). */
 int pk_prover_matvec(pk_prover *p, int which, int transposed, const pk_buf *x, pk_buf *out);
+/* Where the in-tree sponge of pk_prove / pk_prove_seeded / pk_prove_staged runs.  Default (0): ON THE DEVICE
+ * (provekit/common/src/skyscraper/sponge.rs:24-58 restated as device code, csrc/devts.cuh): prover messages are absorbed
+ * and challenges squeezed by one-warp kernels, hints are serialised in HBM, and the host only enqueues work and reads the
+ * proof string with ONE synchronisation at the end.  1: on the host (every challenge is a host round trip; the mode the
+ * callback entry point pk_prove_with_transcript necessarily uses).  Both give the same bytes.  The environment variable
+ * PK_HOST_TRANSCRIPT=1 sets the default for new provers.  pk_prover_host_syncs: stream synchronisations of the last proof. */
+int pk_prover_set_host_transcript(pk_prover *p, int on);
+uint64_t pk_prover_host_syncs(const pk_prover *p);
 /* returns the spongefish NARG string (= WhirR1CSProof.transcript); *out is malloc'd, free with pk_free */
 int pk_prove(pk_prover *p, const uint64_t *witness, const pk_rand *rnd, uint8_t **out, size_t *out_len);
 /* the two halves of pk_prove, exposed so that a caller can keep one proof's inputs resident in HBM:

@@ -106,6 +106,8 @@ def lib() -> ctypes.CDLL:
         "pk_prover_create": (c_int, [vp, POINTER(R1CS), POINTER(vp)]),
         "pk_prover_destroy": (None, [vp]),
         "pk_prover_matvec": (c_int, [vp, c_int, c_int, vp, vp]),
+        "pk_prover_set_host_transcript": (c_int, [vp, c_int]),
+        "pk_prover_host_syncs": (c_uint64, [vp]),
         "pk_prover_shapes": (None, [vp, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
         "pk_prove": (c_int, [vp, u64p, POINTER(Rand), POINTER(vp), POINTER(sz)]),
         "pk_prove_with_transcript": (c_int, [vp, u64p, POINTER(Rand), vp, vp]),

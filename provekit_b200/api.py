@@ -473,6 +473,15 @@ class Prover:
         self.ctx._chk(self.ctx.L.pk_prove_staged(self.h, byref(out), byref(n)))
         return self._take(out, n)
 
+    def set_host_transcript(self, on: bool):
+        """in-tree sponge on the host (True) instead of on the device (default)"""
+        self.ctx._chk(self.ctx.L.pk_prover_set_host_transcript(self.h, 1 if on else 0))
+
+    @property
+    def host_syncs(self) -> int:
+        """stream synchronisations of the last proof"""
+        return int(self.ctx.L.pk_prover_host_syncs(self.h))
+
     def timings(self):
         t = (c_double * 9)()
         self.ctx.L.pk_prover_timings(self.h, t)

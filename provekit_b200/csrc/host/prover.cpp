@@ -16,6 +16,8 @@
 #include <memory>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../pk_internal.h"
 #include "fr_host.h"
 #include "transcript.hpp"
@@ -115,40 +117,6 @@ std::string build_domsep(const WhirCfg& cw, const WhirCfg& ch, int m0) {
     return d.str();
 }
 
-Fr eval_cubic(const Fr c[4], const Fr& x) {  // sumcheck.rs:174-176
-    return pkh::add(c[0], pkh::mul(x, pkh::add(c[1], pkh::mul(x, pkh::add(c[2], pkh::mul(x, c[3]))))));
-}
-void expand_from_univariate(Fr z, int n, Fr* out) {
-    for (int i = 0; i < n; i++) {
-        out[n - 1 - i] = z;
-        z = pkh::sqr(z);
-    }
-}
-// compute_blinding_coefficients_for_round, whir_r1cs.rs:103-171
-void blinding_coeffs_for_round(const Fr* g, int n, int compute_for, const Fr* alphas, Fr out[4]) {
-    bool all_fixed = false;
-    if (compute_for == n) {
-        all_fixed = true;
-        compute_for = n - 1;
-    }
-    Fr prefix = pkh::ZERO, suffix = pkh::ZERO;
-    for (int i = 0; i < compute_for; i++) prefix = pkh::add(prefix, eval_cubic(g + 4 * i, alphas[i]));
-    for (int i = compute_for + 1; i < n; i++)
-        suffix = pkh::add(suffix, pkh::add(eval_cubic(g + 4 * i, pkh::ZERO), eval_cubic(g + 4 * i, pkh::ONE)));
-    Fr pm = pkh::ONE;
-    for (int i = 0; i < n - 1 - compute_for; i++) pm = pkh::dbl(pm);
-    Fr sm = pkh::mul(pm, pkh::half());
-    Fr cst = pkh::add(pkh::mul(pm, prefix), pkh::mul(sm, suffix));
-    const Fr* c = g + 4 * compute_for;
-    Fr r[4] = {pkh::add(pkh::mul(pm, c[0]), cst), pkh::mul(pm, c[1]), pkh::mul(pm, c[2]), pkh::mul(pm, c[3])};
-    if (all_fixed) {
-        out[0] = eval_cubic(r, alphas[compute_for]);
-        out[1] = out[2] = out[3] = pkh::ZERO;
-    } else {
-        std::memcpy(out, r, sizeof r);
-    }
-}
-
 double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -174,23 +142,49 @@ int spmv(pk_ctx* ctx, const DevCsr& M, const void* interned, const void* x, void
 
 }  // namespace
 
+// device + pinned work areas of the protocol flow, one set per prover (one proof at a time per prover)
+constexpr size_t NARG_CAP_WORDS = ((size_t)2 << 20) / 4;  // proof string capacity (m = 23 needs ~0.5 MiB)
+constexpr size_t HINT_WORDS = 72 * 1024;                  // lens + "stir_answers" + "merkle_proof" of one round
+constexpr size_t BOARD_ELEMS = 2048;                      // challenges, round messages and other scalars of one proof
+constexpr size_t PIN_SCALAR_BYTES = 32 * 1024;
+struct FlowMem {
+    char* dev = nullptr;
+    void* ts = nullptr;             // pk::DevTs + proof string
+    char* board = nullptr;
+    uint32_t* hint = nullptr;       // [0,4): lengths; payload area behind
+    uint32_t* stir_bytes = nullptr; // 512 words
+    uint64_t* stir_idx = nullptr;   // OPEN_MAX_QUERIES
+    uint32_t* n_idx = nullptr;
+    pk::PowCtrl* pow = nullptr;
+    uint8_t* pin = nullptr;         // pinned host memory: [scalar staging | hint mirror | DevTs + proof-string mirror]
+    uint8_t *pin_hint = nullptr, *pin_narg = nullptr;
+};
+
 struct pk_prover {
     pk_ctx* ctx = nullptr;
     uint64_t num_constraints = 0, num_witnesses = 0, num_interned = 0;
     int m = 0, m0 = 0, mh = 0;
     WhirCfg cw, ch;
     std::string domsep;
+    pk::fr_arg iv_canonical = {}, half = {};  // sponge IV (Keccak tag of the domain separator, mod p); 1/2 in Montgomery form
+    bool host_transcript = false;             // run the in-tree sponge on the host instead of on the device
     void* d_interned = nullptr;
     DevCsr A, B, At, Bt, Ct;  // rows of A,B for M*z; transposes (CSC) of A,B,C for eq^T*M
     double timings[9] = {0};
     // staged inputs (pk_prover_upload_inputs): [z || mask_w], g_w, [blind || mask_h], g_h in evaluation form
     pk_buf *masked_w = nullptr, *g_w = nullptr, *masked_h = nullptr, *g_h = nullptr;
-    std::vector<Fr> blind;
     bool staged = false;
+    FlowMem mem;
+    uint64_t host_syncs = 0;  // cudaStreamSynchronize calls of the last proof (pk_prover_host_syncs)
     ~pk_prover();  // frees every device allocation, also after a partially failed pk_prover_create
 };
 
 namespace {
+
+struct NvtxRange {  // the reference's tracing spans (SpanStats tree, tooling/cli) as NVTX ranges: an nsys timeline lines up
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // device buffer with RAII over the C-ABI
 struct Buf {
@@ -205,403 +199,530 @@ struct Buf {
     Buf(const Buf&) = delete;
     Buf& operator=(const Buf&) = delete;
     operator pk_buf*() const { return b; }
+    void* d() const { return b->d; }
 };
 using BufP = std::unique_ptr<Buf>;
+
+inline char* el(void* base, long i) { return (char*)base + 32 * i; }  // element i of a device array of field elements
 
 struct Commitment {
     pk_ctx* ctx;
     pk_commitment* c = nullptr;
     int n = 0, batch = 1, domain_log = 0;
-    BufP poly;  // batched coefficients (2^n)
-    Fr ood_point, ood_answer, batching;
+    BufP poly;                                   // batched coefficients (2^n)
+    char *root = nullptr, *ood = nullptr, *ans = nullptr, *batching = nullptr;  // board slots
     explicit Commitment(pk_ctx* x) : ctx(x) {}
     ~Commitment() {
         if (c) pk_commit_free(ctx, c);
     }
 };
 
-class Prover {
+// The protocol flow of WhirR1CSProver::prove.  Every prover message is produced on the device and stays there; what
+// differs between the two transcript modes is only how a message reaches the sponge and how a challenge comes back:
+//   device transcript (fs == nullptr): one-warp kernels on the pk::DevTs in HBM; the host only enqueues, one sync at the end
+//   host transcript   (fs != nullptr): D2H of the message, the caller's (or the in-tree) sponge, H2D of the challenge
+class Flow {
    public:
-    Prover(pk_prover* p, pkh::Transcript& fs) : P(p), ctx(p->ctx), fs(fs) {}
+    Flow(pk_prover* p, pkh::Transcript* fs) : P(p), ctx(p->ctx), fs(fs), dev(fs == nullptr), M(p->mem) {}
     int run();
+    size_t bound_words = 0;  // upper bound of the proof string written so far (device mode: size of the final D2H)
 
    private:
     pk_prover* P;
     pk_ctx* ctx;
-    pkh::Transcript& fs;
+    pkh::Transcript* fs;
+    const bool dev;
+    FlowMem& M;
+    size_t board_used = 0, pin_cursor = 0;
     double* T() { return P->timings; }
+    cudaStream_t st() const { return ctx->stream; }
 
-    int batch_commit(int m, pk_buf* masked_evals, pk_buf* g_evals, Commitment* cm, bool timed);
-    int whir_prove(const WhirCfg& cfg, Commitment* cm, pk_buf* const* weights, const Fr* sums, int n_weights, size_t weights_len);
-    int whir_sumcheck_rounds(BufP (&Pb)[2], BufP (&Wb)[2], int* which, int* cur_log, int rounds, Fr* rs, bool* pending,
-                             Fr* pending_r);
+    char* board(size_t n) {
+        if (board_used + n > BOARD_ELEMS) return nullptr;
+        char* p = M.board + 32 * board_used;
+        board_used += n;
+        return p;
+    }
+    int sync() {
+        PK_CUDA(ctx, cudaStreamSynchronize(st()));
+        P->host_syncs++;
+        pin_cursor = 0;
+        return PK_OK;
+    }
+    int pin_take(size_t bytes, uint8_t** out) {
+        bytes = (bytes + 31) & ~(size_t)31;
+        if (bytes > PIN_SCALAR_BYTES) return pk::set_err(ctx, PK_ERR_INTERNAL, "flow: staging request too large");
+        if (pin_cursor + bytes > PIN_SCALAR_BYTES) PK_TRY(sync());  // earlier async uploads must land before reuse
+        *out = M.pin + pin_cursor;
+        pin_cursor += bytes;
+        return PK_OK;
+    }
+    int exchange(const void* d_absorb, int na, void* d_squeeze, int ns);
+    int challenge_bytes(uint32_t* d_words, int n_bytes);
+    int hint_static(const uint32_t* d_payload, uint32_t words);
+    int hint_open(uint32_t h1max, uint32_t h2max);
     int pow_prove(double bits);
-    size_t stir_queries(int domain_log, int num_queries, std::vector<uint64_t>* idx);
+    int batch_commit(int m, pk_buf* masked_evals, pk_buf* g_evals, Commitment* cm, bool timed);
+    int whir_prove(const WhirCfg& cfg, Commitment* cm, pk_buf* const* weights, int n_weights, size_t weights_len);
 };
 
-int Prover::pow_prove(double bits) {
+// add_scalars(absorb) then challenge_scalars(squeeze); all values are device-resident Montgomery-form field elements
+int Flow::exchange(const void* d_absorb, int na, void* d_squeeze, int ns) {
+    bound_words += 8 * (size_t)na;
+    if (dev) {
+        pk::ProfScope ps(ctx, pk::PROF_OTHER);
+        ctx->launches += pk::launch_ts_exchange(st(), M.ts, d_absorb, na, false, d_squeeze, ns);
+        PK_CUDA(ctx, cudaGetLastError());
+        return PK_OK;
+    }
+    if (na) {
+        uint8_t* h;
+        PK_TRY(pin_take(32 * (size_t)na, &h));
+        PK_CUDA(ctx, cudaMemcpyAsync(h, d_absorb, 32 * (size_t)na, cudaMemcpyDeviceToHost, st()));
+        PK_TRY(sync());
+        std::vector<Fr> v(na);
+        std::memcpy((void*)v.data(), h, 32 * (size_t)na);
+        fs->add_scalars(v.data(), na);
+    }
+    if (ns) {
+        std::vector<Fr> c(ns);
+        fs->challenge_scalars(c.data(), ns);
+        uint8_t* h;
+        PK_TRY(pin_take(32 * (size_t)ns, &h));
+        std::memcpy(h, c.data(), 32 * (size_t)ns);
+        PK_CUDA(ctx, cudaMemcpyAsync(d_squeeze, h, 32 * (size_t)ns, cudaMemcpyHostToDevice, st()));
+    }
+    return PK_OK;
+}
+int Flow::challenge_bytes(uint32_t* d_words, int n_bytes) {
+    if (dev) {
+        pk::ProfScope ps(ctx, pk::PROF_OTHER);
+        ctx->launches += pk::launch_ts_challenge_bytes(st(), M.ts, d_words, n_bytes);
+        PK_CUDA(ctx, cudaGetLastError());
+        return PK_OK;
+    }
+    const size_t padded = ((size_t)n_bytes + 3) & ~(size_t)3;
+    uint8_t* h;
+    PK_TRY(pin_take(padded, &h));
+    std::memset(h, 0, padded);
+    fs->challenge_bytes(h, n_bytes);
+    PK_CUDA(ctx, cudaMemcpyAsync(d_words, h, padded, cudaMemcpyHostToDevice, st()));
+    return PK_OK;
+}
+// ProverState::hint of a payload whose size is known on the host
+int Flow::hint_static(const uint32_t* d_payload, uint32_t words) {
+    bound_words += 1 + (size_t)words;
+    if (dev) {
+        pk::ProfScope ps(ctx, pk::PROF_OTHER);
+        ctx->launches += pk::launch_ts_hint(st(), M.ts, d_payload, words, nullptr);
+        PK_CUDA(ctx, cudaGetLastError());
+        return PK_OK;
+    }
+    PK_CUDA(ctx, cudaMemcpyAsync(M.pin_hint, d_payload, 4 * (size_t)words, cudaMemcpyDeviceToHost, st()));
+    PK_TRY(sync());
+    fs->hint(std::vector<uint8_t>(M.pin_hint, M.pin_hint + 4 * (size_t)words));
+    return PK_OK;
+}
+// the two hints of one opening (k_open_hints): lengths at M.hint[0], M.hint[1], payloads at M.hint + 4 and + 4 + h1max
+int Flow::hint_open(uint32_t h1max, uint32_t h2max) {
+    bound_words += 2 + (size_t)h1max + h2max;
+    if (dev) {
+        pk::ProfScope ps(ctx, pk::PROF_OTHER);
+        ctx->launches += pk::launch_ts_hint(st(), M.ts, M.hint + 4, 0, M.hint);
+        ctx->launches += pk::launch_ts_hint(st(), M.ts, M.hint + 4 + h1max, 0, M.hint + 1);
+        PK_CUDA(ctx, cudaGetLastError());
+        return PK_OK;
+    }
+    const size_t words = 4 + (size_t)h1max + h2max;
+    PK_CUDA(ctx, cudaMemcpyAsync(M.pin_hint, M.hint, 4 * words, cudaMemcpyDeviceToHost, st()));
+    PK_TRY(sync());
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(M.pin_hint);
+    if (w[0] > h1max || w[1] > h2max) return pk::set_err(ctx, PK_ERR_INTERNAL, "flow: hint larger than its bound");
+    const uint8_t* p1 = M.pin_hint + 16;
+    const uint8_t* p2 = p1 + 4 * (size_t)h1max;
+    fs->hint(std::vector<uint8_t>(p1, p1 + 4 * (size_t)w[0]));
+    fs->hint(std::vector<uint8_t>(p2, p2 + 4 * (size_t)w[1]));
+    return PK_OK;
+}
+// [whir] challenge_pow::<SkyscraperPoW>: 32 challenge bytes, grind, 8-byte big-endian nonce (provekit/common/src/
+// skyscraper/pow.rs:14-30 -> skyscraper/core/src/pow.rs:33-41)
+int Flow::pow_prove(double bits) {
     if (bits <= 0) return PK_OK;
+    NvtxRange nv("pow");
     double t0 = now_s();
-    uint8_t ch[32], nb[8];
-    uint64_t c[4], nonce = 0;
-    fs.challenge_bytes(ch, 32);
-    std::memcpy(c, ch, 32);
-    PK_TRY(pk_pow_solve(ctx, c, bits, &nonce));
+    uint64_t thr[4];
+    pk::pow_threshold(bits, thr);
+    // batches above the first hit exit at once and nonces in flight are abandoned between round pairs, so the cost tracks
+    // the winning nonce; small difficulties get small grids (every resident thread hashes at least one nonce)
+    int blocks = 1;
+    const double want = std::exp2(bits + 3.0) / 128.0;
+    while (blocks < 148 * 8 && (double)blocks < want) blocks <<= 1;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    bound_words += 2;
+    if (dev) {
+        pk::ProfScope ps(ctx, pk::PROF_POW);
+        ctx->launches += pk::launch_pow_begin(st(), M.ts, M.pow);
+        ctx->launches += pk::launch_pow_grind(st(), M.pow, pk::to_arg(thr), blocks);
+        ctx->launches += pk::launch_pow_end(st(), M.ts, M.pow);
+        PK_CUDA(ctx, cudaGetLastError());
+        return PK_OK;
+    }
+    uint8_t* h;
+    PK_TRY(pin_take(sizeof(pk::PowCtrl), &h));
+    pk::PowCtrl* c = reinterpret_cast<pk::PowCtrl*>(h);
+    fs->challenge_bytes(reinterpret_cast<uint8_t*>(c->challenge), 32);
+    c->ticket = 0;
+    c->best = ~0ull;
+    PK_CUDA(ctx, cudaMemcpyAsync(M.pow, c, sizeof(pk::PowCtrl), cudaMemcpyHostToDevice, st()));
+    {
+        pk::ProfScope ps(ctx, pk::PROF_POW);
+        ctx->launches += pk::launch_pow_grind(st(), M.pow, pk::to_arg(thr), blocks);
+    }
+    PK_CUDA(ctx, cudaGetLastError());
+    uint8_t* hb;
+    PK_TRY(pin_take(8, &hb));
+    PK_CUDA(ctx, cudaMemcpyAsync(hb, &M.pow->best, 8, cudaMemcpyDeviceToHost, st()));
+    PK_TRY(sync());
+    uint64_t nonce;
+    std::memcpy(&nonce, hb, 8);
+    uint8_t nb[8];
     for (int i = 0; i < 8; i++) nb[i] = (uint8_t)(nonce >> (56 - 8 * i));  // big-endian nonce
-    fs.add_bytes(nb, 8);
+    fs->add_bytes(nb, 8);
     T()[4] += now_s() - t0;
     return PK_OK;
 }
 
-// [whir] get_challenge_stir_queries (recursive-verifier/app/circuit/whir_utilities.go:48-77) + sort/dedup
-size_t Prover::stir_queries(int domain_log, int num_queries, std::vector<uint64_t>* idx) {
-    int folded_log = domain_log - FOLD;
-    int nb = ceil_div(folded_log, 8);
-    std::vector<uint8_t> bytes((size_t)num_queries * nb);
-    fs.challenge_bytes(bytes.data(), bytes.size());
-    idx->resize(num_queries);
-    for (int i = 0; i < num_queries; i++) {
-        uint64_t v = 0;
-        for (int j = 0; j < nb; j++) v = (v << 8) | bytes[(size_t)i * nb + j];
-        (*idx)[i] = v & (((uint64_t)1 << folded_log) - 1);
-    }
-    std::sort(idx->begin(), idx->end());
-    idx->erase(std::unique(idx->begin(), idx->end()), idx->end());
-    return idx->size();
-}
-
-// [whir] CommitmentWriter::commit_batch on the coefficient forms of [f || mask] and g
-int Prover::batch_commit(int m, pk_buf* masked_evals, pk_buf* g_evals, Commitment* cm, bool timed) {
-    size_t N = (size_t)1 << m;
+// batch_commit_to_polynomial (whir_r1cs.rs:182-209) on the staged evaluation vectors [f || mask] and g, then [whir]
+// CommitmentWriter::commit_batch: root -> OOD point -> OOD answers -> batching randomness -> batched polynomial
+int Flow::batch_commit(int m, pk_buf* masked_evals, pk_buf* g_evals, Commitment* cm, bool timed) {
+    NvtxRange nv("batch_commit_to_polynomial");
+    const size_t N = (size_t)1 << m;
     BufP mc(new Buf(ctx, N)), gc(new Buf(ctx, N));
     if (!mc->b || !gc->b) return pk::set_err(ctx, PK_ERR_OOM, "batch_commit: out of device memory");
     PK_TRY(pk_buf_copy(ctx, *mc, 0, masked_evals, 0, N));
     PK_TRY(pk_buf_copy(ctx, *gc, 0, g_evals, 0, N));
     PK_TRY(pk_evals_to_coeffs(ctx, *mc, m));
     PK_TRY(pk_evals_to_coeffs(ctx, *gc, m));
-    const pk_buf* polys[2] = {*mc, *gc};
-    uint64_t root[4];
+    const void* polys[2] = {mc->d(), gc->d()};
+    cm->root = board(1);
+    cm->ood = board(1);
+    cm->ans = board(2);
+    cm->batching = board(1);
+    if (!cm->batching) return pk::set_err(ctx, PK_ERR_INTERNAL, "flow: scalar board exhausted");
     double t0 = now_s();
-    PK_TRY(pk_commit_batch(ctx, polys, 2, m, 1, FOLD, &cm->c, root));
-    if (timed) T()[0] += now_s() - t0;  // NTT + Merkle of the big commitment (split by CUDA events in bench.py)
+    PK_TRY(pk::commit_batch_dev(ctx, polys, 2, m, 1, &cm->c, cm->root));
     cm->n = m;
     cm->batch = 2;
     cm->domain_log = m + 1;
-    Fr rootf;
-    std::memcpy(rootf.l, root, 32);
-    fs.add_scalars(&rootf, 1);
-    fs.challenge_scalars(&cm->ood_point, 1);
-    Fr ans[2];
-    PK_TRY(pk_eval_univariate_batch(ctx, polys, 2, N, cm->ood_point.l, ans[0].l));
-    fs.add_scalars(ans, 2);
-    fs.challenge_scalars(&cm->batching, 1);
-    PK_TRY(pk_axpy(ctx, *mc, *gc, cm->batching.l, N));  // batched polynomial p0 + b*p1
-    cm->ood_answer = pkh::add(ans[0], pkh::mul(cm->batching, ans[1]));
+    PK_TRY(exchange(cm->root, 1, cm->ood, 1));
+    if (timed && !dev) T()[0] += now_s() - t0;  // NTT + Merkle of the big commitment (split by CUDA events in bench.py)
+    PK_TRY(pk::dev_eval_univariate(ctx, polys, 2, N, cm->ood, cm->ans));
+    PK_TRY(exchange(cm->ans, 2, cm->batching, 1));
+    {   // batched polynomial p0 + b*p1
+        pk::ProfScope ps(ctx, pk::PROF_OTHER);
+        ctx->launches += pk::launch_axpy(st(), mc->d(), gc->d(), pk::fr_arg(), cm->batching, N);
+    }
+    PK_CUDA(ctx, cudaGetLastError());
     cm->poly = std::move(mc);
     return PK_OK;
 }
 
-int Prover::whir_sumcheck_rounds(BufP (&Pb)[2], BufP (&Wb)[2], int* which, int* cur_log, int rounds, Fr* rs, bool* pending,
-                                 Fr* pending_r) {
-    double t0 = now_s();
-    for (int i = 0; i < rounds; i++) {
-        Fr h[3];
-        int w = *which;
-        if (*pending) {
-            PK_TRY(pk_whir_sumcheck_round(ctx, *Pb[w], *Wb[w], *Pb[1 - w], *Wb[1 - w], *cur_log, pending_r->l, h[0].l));
-            *which = 1 - w;
-            (*cur_log)--;
-        } else {
-            PK_TRY(pk_whir_sumcheck_round(ctx, *Pb[w], *Wb[w], nullptr, nullptr, *cur_log, nullptr, h[0].l));
-        }
-        fs.add_scalars(h, 3);
-        fs.challenge_scalars(&rs[i], 1);
-        *pending = true;
-        *pending_r = rs[i];
-    }
-    T()[3] += now_s() - t0;
-    return PK_OK;
-}
-
-// [whir] Prover::prove
+// [whir] Prover::prove (message order restated from recursive-verifier/app/circuit/whir.go:51-220)
 // weights_len: the linear weights vanish beyond their first weights_len elements (zero-extended R1CS rows)
-int Prover::whir_prove(const WhirCfg& cfg, Commitment* cm, pk_buf* const* weights, const Fr* sums, int n_weights,
-                       size_t weights_len) {
+int Flow::whir_prove(const WhirCfg& cfg, Commitment* cm, pk_buf* const* weights, int n_weights, size_t weights_len) {
+    NvtxRange nv("run_zk_whir_pcs_prover");
     const int n = cfg.num_variables;
     const size_t N = (size_t)1 << n;
     if (weights_len == 0 || weights_len > N) weights_len = N;
-    Fr gamma, g = pkh::ONE;
-    fs.challenge_scalars(&gamma, 1);
+    char* gamma = board(1);
+    char* gpow = board(3);
+    char* h3 = board(3);
+    char* RR = board(n);  // folding randomness, NEWEST FIRST: challenge number t lives at RR[n-1-t]
+    char* dv = board(3);
+    if (!dv) return pk::set_err(ctx, PK_ERR_INTERNAL, "flow: scalar board exhausted");
+    PK_TRY(exchange(nullptr, 0, gamma, 1));
+    ctx->launches += pk::launch_powers(st(), gpow, gamma, n_weights, 1, nullptr);
     BufP Pb[2] = {BufP(new Buf(ctx, N)), BufP(new Buf(ctx, N / 2))};
     BufP Wb[2] = {BufP(new Buf(ctx, N)), BufP(new Buf(ctx, N / 2))};
     if (!Pb[0]->b || !Pb[1]->b || !Wb[0]->b || !Wb[1]->b) return pk::set_err(ctx, PK_ERR_OOM, "whir_prove: out of device memory");
     PK_TRY(pk_buf_zero(ctx, *Wb[0], 0, N));
-    std::vector<Fr> pt(n);
-    expand_from_univariate(cm->ood_point, n, pt.data());
-    PK_TRY(pk_eval_eq(ctx, pt[0].l, n, g.l, *Wb[0]));  // OOD constraint goes first
-    for (int j = 0; j < n_weights; j++) {
-        g = pkh::mul(g, gamma);
-        PK_TRY(pk_axpy(ctx, *Wb[0], weights[j], g.l, weights_len));
+    // W = eq(pow(ood_point), .) + sum_j gamma^(j+1) w_j : the OOD constraint goes first
+    PK_TRY(pk::dev_eval_eq(ctx, cm->ood, pk::TENSOR_PTS_UNIVARIATE, n, nullptr, Wb[0]->d()));
+    {
+        pk::ProfScope ps(ctx, pk::PROF_OTHER);
+        for (int j = 0; j < n_weights; j++)
+            ctx->launches += pk::launch_axpy(st(), Wb[0]->d(), weights[j]->d, pk::fr_arg(), el(gpow, j), weights_len);
     }
-    (void)sums;  // the claimed sum only enters the verifier's checks; h(0), h(1), h(2) are computed directly
     PK_TRY(pk_buf_copy(ctx, *Pb[0], 0, *cm->poly, 0, N));
     PK_TRY(pk_coeffs_to_evals(ctx, *Pb[0], n));
 
-    std::vector<Fr> all_r;
-    int which = 0, cur_log = n;
-    bool pending = false;
-    Fr pending_r = pkh::ZERO, fold_r[FOLD];
-    PK_TRY(whir_sumcheck_rounds(Pb, Wb, &which, &cur_log, FOLD, fold_r, &pending, &pending_r));
-    all_r.insert(all_r.end(), fold_r, fold_r + FOLD);
+    int which = 0, cur_log = n, t = 0;  // t: folding challenges drawn so far
+    bool pending = false;               // the fold by challenge t-1 has not been applied to P, W yet
+    // one sumcheck round = (fold by the previous challenge, fused) + [h(0), h(1), h(2)] -> transcript -> next challenge
+    auto sumcheck_rounds = [&](int rounds) -> int {
+        double t0 = now_s();
+        for (int i = 0; i < rounds; i++) {
+            const int w = which;
+            {
+                pk::ProfScope ps(ctx, pk::PROF_WHIR_SUMCHECK);
+                if (pending) {
+                    ctx->launches += pk::launch_whir_sumcheck_round(st(), Pb[w]->d(), Wb[w]->d(), Pb[1 - w]->d(), Wb[1 - w]->d(), cur_log,
+                                                                  true, pk::fr_arg(), el(RR, n - t), ctx->d_partials, h3);
+                    which = 1 - w;
+                    cur_log--;
+                } else {
+                    ctx->launches += pk::launch_whir_sumcheck_round(st(), Pb[w]->d(), Wb[w]->d(), nullptr, nullptr, cur_log, false,
+                                                                  pk::fr_arg(), nullptr, ctx->d_partials, h3);
+                }
+            }
+            PK_CUDA(ctx, cudaGetLastError());
+            PK_TRY(exchange(h3, 3, el(RR, n - 1 - t), 1));
+            t++;
+            pending = true;
+        }
+        if (!dev) T()[3] += now_s() - t0;
+        return PK_OK;
+    };
+    PK_TRY(sumcheck_rounds(FOLD));
 
-    BufP coeffs;              // folded coefficient list of the current round (null: still cm->poly)
-    pk_buf* cur_coeffs = *cm->poly;
-    int nv = n, domain_log = cm->domain_log;
+    BufP coeffs;                       // folded coefficient list of the current round (null: still cm->poly)
+    const void* cur_coeffs = cm->poly->d();
+    int nv_ = n, domain_log = cm->domain_log;
     pk_commitment* prev = cm->c;
     std::unique_ptr<Commitment> prev_owned;
     for (int ri = 0; ri <= cfg.n_rounds; ri++) {
         const bool is_final = ri == cfg.n_rounds;
-        const int nvp = nv - FOLD;
+        const int nvp = nv_ - FOLD;
         BufP folded(new Buf(ctx, (size_t)1 << nvp));
         if (!folded->b) return pk::set_err(ctx, PK_ERR_OOM, "whir_prove: out of device memory");
-        PK_TRY(pk_fold_coeffs(ctx, cur_coeffs, nv, fold_r[0].l, FOLD, *folded));
+        {   // CoefficientList::fold by the four challenges of this block (r[j] binds bit j): RR is newest-first, stride -1
+            pk::ProfScope ps(ctx, pk::PROF_OTHER);
+            ctx->launches += pk::launch_fold_coeffs(st(), cur_coeffs, nv_, el(RR, n - 1 - FOLD * ri), -1, FOLD, folded->d());
+        }
+        PK_CUDA(ctx, cudaGetLastError());
         std::unique_ptr<Commitment> next;
-        Fr ood_pt = pkh::ZERO, ood_ans = pkh::ZERO;
+        char* ood_pt = nullptr;
         double pow_bits;
         int nq;
         if (!is_final) {
             const RoundCfg& rc = cfg.rounds[ri];
             const int new_dl = domain_log - 1;
             next.reset(new Commitment(ctx));
-            const pk_buf* polys[1] = {*folded};
-            uint64_t root[4];
-            PK_TRY(pk_commit_batch(ctx, polys, 1, nvp, new_dl - nvp, FOLD, &next->c, root));
+            next->root = board(1);
+            ood_pt = board(1);
+            char* ood_ans = board(1);
+            if (!ood_ans) return pk::set_err(ctx, PK_ERR_INTERNAL, "flow: scalar board exhausted");
+            const void* polys[1] = {folded->d()};
+            PK_TRY(pk::commit_batch_dev(ctx, polys, 1, nvp, new_dl - nvp, &next->c, next->root));
             next->n = nvp;
             next->domain_log = new_dl;
-            Fr rootf;
-            std::memcpy(rootf.l, root, 32);
-            fs.add_scalars(&rootf, 1);
-            fs.challenge_scalars(&ood_pt, 1);
-            PK_TRY(pk_eval_univariate(ctx, *folded, (size_t)1 << nvp, ood_pt.l, ood_ans.l));
-            fs.add_scalars(&ood_ans, 1);
+            PK_TRY(exchange(next->root, 1, ood_pt, 1));
+            PK_TRY(pk::dev_eval_univariate(ctx, polys, 1, (size_t)1 << nvp, ood_pt, ood_ans));
+            PK_TRY(exchange(ood_ans, 1, nullptr, 0));
             pow_bits = rc.pow_bits;
             nq = rc.num_queries;
         } else {
-            std::vector<Fr> fc((size_t)1 << nvp);
-            PK_TRY(pk_buf_download(ctx, *folded, 0, fc[0].l, fc.size()));
-            fs.add_scalars(fc.data(), fc.size());
+            PK_TRY(exchange(folded->d(), 1 << nvp, nullptr, 0));  // the final coefficients go out in the clear
             pow_bits = cfg.final_pow_bits;
             nq = cfg.final_queries;
         }
         PK_TRY(pow_prove(pow_bits));
         double t_open = now_s();
-        std::vector<uint64_t> idx;
-        const size_t nidx = stir_queries(domain_log, nq, &idx);
-        const size_t w = pk_commit_leaf_width(prev);
-        const int depth = domain_log - FOLD;
-        std::vector<Fr> leaves(nidx * w), sib(nidx), suf(nidx * (size_t)(depth > 0 ? depth : 1));
-        std::vector<uint64_t> pre(nidx), slen(nidx);
-        PK_TRY(pk_commit_open(ctx, prev, idx.data(), nidx, leaves[0].l, sib[0].l, pre.data(), suf[0].l, slen.data(), suf.size()));
-        {   // hint stir_answers: Vec<Vec<F>>
-            std::vector<uint8_t> hb;
-            hb.reserve(16 + nidx * (8 + w * 32));
-            pkh::put_u64(hb, nidx);
-            for (size_t q = 0; q < nidx; q++) {
-                pkh::put_u64(hb, w);
-                for (size_t k = 0; k < w; k++) pkh::put_fr(hb, leaves[q * w + k]);
+        {   // STIR queries into the previous oracle, answers and Merkle multi-proof as hints
+            NvtxRange nvo("stir_open");
+            const int folded_log = domain_log - FOLD, nb = ceil_div(folded_log, 8);
+            if (nq > pk::OPEN_MAX_QUERIES || nq * nb > 2048)
+                return pk::set_err(ctx, PK_ERR_INTERNAL, "whir_prove: %d queries exceed the device work areas", nq);
+            PK_TRY(challenge_bytes(M.stir_bytes, nq * nb));
+            const uint32_t w = (uint32_t)prev->w, depth = (uint32_t)prev->depth, q = (uint32_t)nq;
+            const uint32_t h1max = 2 + q * (2 + 8 * w);
+            const uint32_t h2max = (2 + 8 * q) + (2 + 2 * q) + (2 + 2 * q + 8 * q * (depth > 1 ? depth - 1 : 0)) + (2 + 2 * q);
+            if (4 + (size_t)h1max + h2max > HINT_WORDS) return pk::set_err(ctx, PK_ERR_INTERNAL, "whir_prove: hints exceed the work area");
+            {
+                pk::ProfScope ps(ctx, pk::PROF_OTHER);
+                ctx->launches += pk::launch_stir_indices(st(), M.stir_bytes, nq, nb, folded_log, M.stir_idx, M.n_idx);
+                ctx->launches += pk::launch_open_hints(st(), prev->leaves, prev->canonical_leaves, (int)w, prev->nodes, prev->L, (int)depth,
+                                                     M.stir_idx, M.n_idx, M.hint + 4, M.hint + 4 + h1max, M.hint);
             }
-            fs.hint(hb);
+            PK_CUDA(ctx, cudaGetLastError());
+            PK_TRY(hint_open(h1max, h2max));
         }
-        {   // hint merkle_proof: ark MultiPath (digests already canonical)
-            std::vector<uint8_t> hb;
-            pkh::put_u64(hb, nidx);
-            for (size_t q = 0; q < nidx; q++) pkh::put_canonical(hb, sib[q].l);
-            pkh::put_u64(hb, nidx);
-            for (size_t q = 0; q < nidx; q++) pkh::put_u64(hb, pre[q]);
-            pkh::put_u64(hb, nidx);
-            size_t pos = 0;
-            for (size_t q = 0; q < nidx; q++) {
-                pkh::put_u64(hb, slen[q]);
-                for (uint64_t d = 0; d < slen[q]; d++) pkh::put_canonical(hb, suf[pos++].l);
-            }
-            pkh::put_u64(hb, nidx);
-            for (size_t q = 0; q < nidx; q++) pkh::put_u64(hb, idx[q]);
-            fs.hint(hb);
-        }
-        T()[5] += now_s() - t_open;
+        if (!dev) T()[5] += now_s() - t_open;
         if (!is_final) {
-            Fr gam, gp = pkh::ONE;
-            fs.challenge_scalars(&gam, 1);
+            char* gam = board(1);
+            char* sc = board((size_t)nq + 1);
+            if (!sc) return pk::set_err(ctx, PK_ERR_INTERNAL, "flow: scalar board exhausted");
+            PK_TRY(exchange(nullptr, 0, gam, 1));
+            // combination scalars 1, gam, gam^2, ..: the OOD point first, then the (de-duplicated) STIR points
+            ctx->launches += pk::launch_powers(st(), sc, gam, nq + 1, 0, M.n_idx);
             // the fold by the last challenge must land before new equality weights are added
             if (pending) {
-                Fr dummy[3];
-                PK_TRY(pk_whir_sumcheck_round(ctx, *Pb[which], *Wb[which], *Pb[1 - which], *Wb[1 - which], cur_log, pending_r.l,
-                                              dummy[0].l));
+                pk::ProfScope ps(ctx, pk::PROF_WHIR_SUMCHECK);
+                ctx->launches += pk::launch_whir_sumcheck_round(st(), Pb[which]->d(), Wb[which]->d(), Pb[1 - which]->d(), Wb[1 - which]->d(),
+                                                              cur_log, true, pk::fr_arg(), el(RR, n - t), ctx->d_partials, ctx->d_result);
                 which = 1 - which;
                 cur_log--;
                 pending = false;
             }
-            // new equality constraints, scaled by 1, gam, gam^2, ..: the OOD point, then the STIR points
-            // z_q = (domain_gen^16)^idx[q] = omega_D^idx[q] on the folded domain D = 2^(domain_log - 4)
-            // (recursive-verifier/app/circuit/whir.go:139-142).  The STIR batch goes through the sparse-DFT form.
-            std::vector<Fr> pts((size_t)nvp), sc(nidx + 1);
-            expand_from_univariate(ood_pt, nvp, pts.data());
-            sc[0] = gp;
-            for (size_t q = 0; q < nidx; q++) {
-                gp = pkh::mul(gp, gam);
-                sc[q + 1] = gp;
-            }
-            // (the folded STIR values only enter the verifier's claimed sum, not the prover's messages)
-            PK_TRY(pk_eval_eq(ctx, pts[0].l, nvp, sc[0].l, *Wb[which]));
-            PK_TRY(pk_eval_eq_roots_batch(ctx, idx.data(), nidx, domain_log - FOLD, nvp, sc[1].l, *Wb[which]));
-            PK_TRY(whir_sumcheck_rounds(Pb, Wb, &which, &cur_log, FOLD, fold_r, &pending, &pending_r));
-            all_r.insert(all_r.end(), fold_r, fold_r + FOLD);
+            // new equality constraints: the OOD point, then the STIR points z_q = omega_D^idx[q] on the folded domain
+            // D = 2^(domain_log - 4) (recursive-verifier/app/circuit/whir.go:139-142); large batches take the sparse-DFT form
+            PK_TRY(pk::dev_eval_eq(ctx, ood_pt, pk::TENSOR_PTS_UNIVARIATE, nvp, sc, Wb[which]->d()));
+            PK_TRY(pk::dev_eval_eq_roots(ctx, M.stir_idx, M.n_idx, (size_t)nq, domain_log - FOLD, nvp, el(sc, 1), Wb[which]->d()));
+            PK_TRY(sumcheck_rounds(FOLD));
         } else {
-            Fr fr_r[FOLD];
-            PK_TRY(whir_sumcheck_rounds(Pb, Wb, &which, &cur_log, cfg.final_sumcheck_rounds, fr_r, &pending, &pending_r));
-            all_r.insert(all_r.end(), fr_r, fr_r + cfg.final_sumcheck_rounds);
+            PK_TRY(sumcheck_rounds(cfg.final_sumcheck_rounds));
         }
         coeffs = std::move(folded);
-        cur_coeffs = *coeffs;
-        nv = nvp;
+        cur_coeffs = coeffs->d();
+        nv_ = nvp;
         if (!is_final) {
             prev_owned = std::move(next);
             prev = prev_owned->c;
             domain_log -= 1;
         }
     }
-    // deferred weight evaluations at the reversed folding randomness
-    std::vector<Fr> R(n, pkh::ZERO);
-    for (int i = 0; i < n && i < (int)all_r.size(); i++) R[i] = all_r[all_r.size() - 1 - i];
-    std::vector<uint8_t> hb;
-    pkh::put_u64(hb, (uint64_t)n_weights);
-    Fr dv[3];
-    PK_TRY(pk_mle_eval_batch_prefix(ctx, weights, n_weights, n, weights_len, R[0].l, dv[0].l));
-    for (int j = 0; j < n_weights; j++) pkh::put_fr(hb, dv[j]);
-    fs.hint(hb);
+    // deferred weight evaluations at the reversed folding randomness (RR is stored reversed already)
+    const void* wp[3] = {nullptr, nullptr, nullptr};
+    for (int j = 0; j < n_weights; j++) wp[j] = weights[j]->d;
+    PK_TRY(pk::dev_mle_eval_prefix(ctx, wp, n_weights, n, weights_len, RR, dv));
+    ctx->launches += pk::launch_hint_scalars(st(), M.hint + 4, dv, 1, n_weights, 1, 0);
+    PK_TRY(hint_static(M.hint + 4, 2 + 8 * (uint32_t)n_weights));
     return PK_OK;
 }
 
-int Prover::run() {
+int Flow::run() {
+    NvtxRange nv("prove");
     const double t_start = now_s();
     const int m = P->m, m0 = P->m0, mh = P->mh;
-    const size_t N = (size_t)1 << m, N0 = (size_t)1 << m0;
+    const size_t N = (size_t)1 << m, N0 = (size_t)1 << m0, Nh = (size_t)1 << mh;
     const size_t nw = P->num_witnesses, nc = P->num_constraints;
+    P->host_syncs = 0;
+    if (dev) {
+        ctx->launches += pk::launch_ts_init(st(), M.ts, P->iv_canonical, (uint32_t)NARG_CAP_WORDS);
+        PK_CUDA(ctx, cudaGetLastError());
+    }
     // [f || mask] and g in evaluation form were staged by pk_prover_upload_inputs
     pk_buf *masked_w = P->masked_w, *g_w = P->g_w, *masked_h = P->masked_h, *g_h = P->g_h;
     Commitment cmw(ctx);
     PK_TRY(batch_commit(m, masked_w, g_w, &cmw, true));
 
-    // ---- zk-sumcheck (run_zk_sumcheck_prover) ----
-    std::vector<Fr> r(m0), alpha(m0);
-    fs.challenge_scalars(r.data(), m0);
+    // ---- zk-sumcheck (run_zk_sumcheck_prover, whir_r1cs.rs:228-369) ----
+    char* r = board(m0);
+    char* alpha = board(m0);
+    pk::ZkGlue G = {};
+    G.blind = (const pk::fr*)masked_h->d;  // the 4 m_0 blinding coefficients open the staged [blind || mask_h] vector
+    G.suffix = (pk::fr*)board(m0);
+    G.state = (pk::fr*)board(4);
+    G.alpha = (pk::fr*)alpha;
+    G.h3 = (pk::fr*)board(3);
+    G.cf = (pk::fr*)board(4);
+    G.m0 = m0;
+    char* fg = board(2);
+    char* fg6 = board(6);
+    if (!fg6) return pk::set_err(ctx, PK_ERR_INTERNAL, "flow: scalar board exhausted");
     Buf a(ctx, N0), b(ctx, N0), c(ctx, N0), eq(ctx, N0);
     if (!a.b || !b.b || !c.b || !eq.b) return pk::set_err(ctx, PK_ERR_OOM, "prove: out of device memory");
-    double t0 = now_s();
-    PK_TRY(pk_buf_zero(ctx, a, 0, N0));
-    PK_TRY(pk_buf_zero(ctx, b, 0, N0));
-    PK_TRY(pk_buf_zero(ctx, c, 0, N0));
-    PK_TRY(pk_buf_zero(ctx, eq, 0, N0));
-    // calculate_witness_bounds (sumcheck.rs:181-193): a = A z, b = B z, c = a o b; z = first nw of masked_w
-    PK_TRY(spmv(ctx, P->A, P->d_interned, masked_w->d, a.b->d, nc));
-    PK_TRY(spmv(ctx, P->B, P->d_interned, masked_w->d, b.b->d, nc));
-    ctx->launches += pk::launch_mul(ctx->stream, a.b->d, b.b->d, c.b->d, nc);
-    PK_TRY(pk_eval_eq(ctx, r[0].l, m0, pkh::ONE.l, eq));
-    T()[6] += now_s() - t0;
-
-    const Fr* blind = P->blind.data();
-    const size_t Nh = (size_t)1 << mh;
     Commitment cmh(ctx);
-    PK_TRY(batch_commit(mh, masked_h, g_h, &cmh, false));
-
-    Fr c0[4];
-    blinding_coeffs_for_round(blind, m0, 0, nullptr, c0);
-    Fr sum_g = pkh::add(eval_cubic(c0, pkh::ZERO), eval_cubic(c0, pkh::ONE));  // sum_over_hypercube
-    fs.add_scalars(&sum_g, 1);
-    Fr rho;
-    fs.challenge_scalars(&rho, 1);
-    Fr saved = pkh::mul(rho, sum_g);
-    const Fr HALF = pkh::half();
-    int cur = m0;
-    t0 = now_s();
-    for (int idx = 0; idx < m0; idx++) {
-        Fr h3[3];
-        PK_TRY(pk_zk_sumcheck_round(ctx, a, b, c, eq, cur, idx ? alpha[idx - 1].l : nullptr, h3[0].l));
-        if (idx) cur--;
-        Fr gp[4], cf[4];
-        blinding_coeffs_for_round(blind, m0, idx, alpha.data(), gp);
-        cf[0] = pkh::add(h3[0], pkh::mul(rho, gp[0]));
-        Fr g_m1 = pkh::sub(pkh::add(pkh::sub(gp[0], gp[1]), gp[2]), gp[3]);
-        Fr c_m1 = pkh::add(h3[1], pkh::mul(rho, g_m1));
-        cf[2] = pkh::mul(HALF, pkh::sub(pkh::sub(pkh::sub(pkh::add(saved, c_m1), cf[0]), cf[0]), cf[0]));
-        cf[3] = pkh::add(h3[2], pkh::mul(rho, gp[3]));
-        cf[1] = pkh::sub(pkh::sub(pkh::sub(pkh::sub(saved, cf[0]), cf[0]), cf[3]), cf[2]);
-        // whir_r1cs.rs:326-333: the round identity the reference asserts
-        Fr chk = pkh::add(pkh::add(pkh::add(pkh::add(cf[0], cf[0]), cf[1]), cf[2]), cf[3]);
-        if (chk != saved) return pk::set_err(ctx, PK_ERR_INTERNAL, "zk-sumcheck round %d identity failed", idx);
-        fs.add_scalars(cf, 4);
-        fs.challenge_scalars(&alpha[idx], 1);
-        saved = eval_cubic(cf, alpha[idx]);
-    }
-    T()[2] += now_s() - t0;
-
-    {   // statement over the blinding commitment: weight = expand_powers(alpha), zero-extended
-        std::vector<Fr> wt(Nh, pkh::ZERO);
-        for (int i = 0; i < m0; i++) {
-            wt[4 * i] = pkh::ONE;
-            wt[4 * i + 1] = alpha[i];
-            wt[4 * i + 2] = pkh::sqr(alpha[i]);
-            wt[4 * i + 3] = pkh::mul(wt[4 * i + 2], alpha[i]);
+    {
+        NvtxRange nvz("run_zk_sumcheck_prover");
+        PK_TRY(exchange(nullptr, 0, r, m0));
+        double t0 = now_s();
+        {
+            NvtxRange nvb("calculate_witness_bounds");
+            PK_TRY(pk_buf_zero(ctx, a, 0, N0));
+            PK_TRY(pk_buf_zero(ctx, b, 0, N0));
+            PK_TRY(pk_buf_zero(ctx, c, 0, N0));
+            // sumcheck.rs:181-193: a = A z, b = B z, c = a o b; z = first nw of masked_w
+            pk::ProfScope ps(ctx, pk::PROF_OTHER);
+            PK_TRY(spmv(ctx, P->A, P->d_interned, masked_w->d, a.d(), nc));
+            PK_TRY(spmv(ctx, P->B, P->d_interned, masked_w->d, b.d(), nc));
+            ctx->launches += pk::launch_mul(st(), a.d(), b.d(), c.d(), nc);
         }
+        {
+            NvtxRange nve("calculate_evaluations_over_boolean_hypercube_for_eq");
+            PK_TRY(pk_buf_zero(ctx, eq, 0, N0));
+            PK_TRY(pk::dev_eval_eq(ctx, r, pk::TENSOR_PTS_EXPLICIT, m0, nullptr, eq.d()));
+        }
+        if (!dev) T()[6] += now_s() - t0;
+
+        PK_TRY(batch_commit(mh, masked_h, g_h, &cmh, false));
+        {
+            pk::ProfScope ps(ctx, pk::PROF_OTHER);
+            ctx->launches += pk::launch_zk_init(st(), G, P->half);
+        }
+        PK_TRY(exchange(el(G.state, 3), 1, el(G.state, 0), 1));  // sum of g over the hypercube -> rho
+        int cur = m0;
+        t0 = now_s();
+        for (int idx = 0; idx < m0; idx++) {
+            {
+                pk::ProfScope ps(ctx, pk::PROF_ZK_SUMCHECK);
+                ctx->launches += pk::launch_zk_sumcheck_round(st(), a.d(), b.d(), c.d(), eq.d(), cur, idx > 0, pk::fr_arg(),
+                                                            idx > 0 ? el(alpha, idx - 1) : nullptr, ctx->d_partials, G.h3);
+            }
+            if (idx) cur--;
+            {   // blinded cubic of the round: 4 coefficients out, alpha_idx back (whir_r1cs.rs:300-345)
+                pk::ProfScope ps(ctx, pk::PROF_OTHER);
+                ctx->launches += pk::launch_zk_glue(st(), G, idx, P->half, dev ? M.ts : nullptr);
+            }
+            PK_CUDA(ctx, cudaGetLastError());
+            if (dev)
+                bound_words += 32;
+            else
+                PK_TRY(exchange(G.cf, 4, el(alpha, idx), 1));
+        }
+        if (!dev) T()[2] += now_s() - t0;
+
+        // statement over the blinding commitment: weight = expand_powers(alpha), zero-extended (whir_r1cs.rs:347-377)
         Buf dw(ctx, Nh);
         if (!dw.b) return pk::set_err(ctx, PK_ERR_OOM, "prove: out of device memory");
-        PK_TRY(pk_buf_upload(ctx, dw, 0, wt[0].l, Nh));
-        Fr fg[2];
-        const pk_buf* wa[1] = {dw};
-        const pk_buf* fb[2] = {masked_h, g_h};
-        PK_TRY(pk_multi_dot(ctx, wa, 1, fb, 2, Nh, fg[0].l));
-        Fr stmt = pkh::add(fg[0], pkh::mul(cmh.batching, fg[1]));
-        fs.add_scalars(fg, 2);
+        {
+            pk::ProfScope ps(ctx, pk::PROF_OTHER);
+            ctx->launches += pk::launch_expand_powers(st(), dw.d(), alpha, m0, Nh);
+            const void* wa[1] = {dw.d()};
+            const void* fb[2] = {masked_h->d, g_h->d};
+            ctx->launches += pk::launch_multi_dot(st(), wa, 1, fb, 2, Nh, ctx->d_partials, fg);
+        }
+        PK_CUDA(ctx, cudaGetLastError());
+        PK_TRY(exchange(fg, 2, nullptr, 0));
         pk_buf* ws[1] = {dw};
-        PK_TRY(whir_prove(P->ch, &cmh, ws, &stmt, 1, 0));
+        PK_TRY(whir_prove(P->ch, &cmh, ws, 1, 0));
     }
 
     // ---- weights from the R1CS instance: eq(alpha)^T * {A,B,C}, zero-extended to 2^m ----
-    t0 = now_s();
-    Buf eq_alpha(ctx, N0);
+    double t0 = now_s();
     BufP wts[3] = {BufP(new Buf(ctx, N)), BufP(new Buf(ctx, N)), BufP(new Buf(ctx, N))};
-    if (!eq_alpha.b || !wts[0]->b || !wts[1]->b || !wts[2]->b) return pk::set_err(ctx, PK_ERR_OOM, "prove: out of device memory");
-    PK_TRY(pk_buf_zero(ctx, eq_alpha, 0, N0));
-    PK_TRY(pk_eval_eq(ctx, alpha[0].l, m0, pkh::ONE.l, eq_alpha));
-    const DevCsr* T3[3] = {&P->At, &P->Bt, &P->Ct};
-    Fr f_sums[3], g_sums[3], stmts[3], fg6[6];
-    for (int j = 0; j < 3; j++) {
-        PK_TRY(pk_buf_zero(ctx, *wts[j], 0, N));
-        PK_TRY(spmv(ctx, *T3[j], P->d_interned, eq_alpha.b->d, wts[j]->b->d, nw));
+    {
+        NvtxRange nvr("calculate_external_row_of_r1cs_matrices");
+        Buf eq_alpha(ctx, N0);
+        if (!eq_alpha.b || !wts[0]->b || !wts[1]->b || !wts[2]->b) return pk::set_err(ctx, PK_ERR_OOM, "prove: out of device memory");
+        PK_TRY(pk_buf_zero(ctx, eq_alpha, 0, N0));
+        PK_TRY(pk::dev_eval_eq(ctx, alpha, pk::TENSOR_PTS_EXPLICIT, m0, nullptr, eq_alpha.d()));
+        const DevCsr* T3[3] = {&P->At, &P->Bt, &P->Ct};
+        for (int j = 0; j < 3; j++) {
+            PK_TRY(pk_buf_zero(ctx, *wts[j], 0, N));
+            pk::ProfScope ps(ctx, pk::PROF_OTHER);
+            PK_TRY(spmv(ctx, *T3[j], P->d_interned, eq_alpha.d(), wts[j]->d(), nw));
+        }
+        // the weights vanish beyond the witness: num_witnesses terms suffice for <w_j, f> and <w_j, g>
+        pk::ProfScope ps(ctx, pk::PROF_OTHER);
+        const void* wa[3] = {wts[0]->d(), wts[1]->d(), wts[2]->d()};
+        const void* fb[2] = {masked_w->d, g_w->d};
+        ctx->launches += pk::launch_multi_dot(st(), wa, 3, fb, 2, nw, ctx->d_partials, fg6);
+        // hint claimed_evaluations: (Vec<F>, Vec<F>) = (f_sums, g_sums); fg6 holds them interleaved
+        ctx->launches += pk::launch_hint_scalars(st(), M.hint + 4, fg6, 2, 3, 2, 1);
     }
-    {   // the weights vanish beyond the witness: num_witnesses terms suffice for <w_j, f> and <w_j, g>
-        const pk_buf* wa[3] = {*wts[0], *wts[1], *wts[2]};
-        const pk_buf* fb[2] = {masked_w, g_w};
-        PK_TRY(pk_multi_dot(ctx, wa, 3, fb, 2, nw, fg6[0].l));
-    }
-    for (int j = 0; j < 3; j++) {
-        f_sums[j] = fg6[2 * j];
-        g_sums[j] = fg6[2 * j + 1];
-        stmts[j] = pkh::add(f_sums[j], pkh::mul(cmw.batching, g_sums[j]));
-    }
-    T()[6] += now_s() - t0;
-    {   // hint claimed_evaluations: (Vec<F>, Vec<F>)
-        std::vector<uint8_t> hb;
-        pkh::put_u64(hb, 3);
-        for (int j = 0; j < 3; j++) pkh::put_fr(hb, f_sums[j]);
-        pkh::put_u64(hb, 3);
-        for (int j = 0; j < 3; j++) pkh::put_fr(hb, g_sums[j]);
-        fs.hint(hb);
-    }
+    PK_CUDA(ctx, cudaGetLastError());
+    if (!dev) T()[6] += now_s() - t0;
+    PK_TRY(hint_static(M.hint + 4, 2 * (2 + 8 * 3)));
     pk_buf* ws[3] = {*wts[0], *wts[1], *wts[2]};
-    PK_TRY(whir_prove(P->cw, &cmw, ws, stmts, 3, nw));
-    PK_TRY(pk_ctx_sync(ctx));
-    if (!fs.ok()) return pk::set_err(ctx, PK_ERR_INVALID_ARG, "prove: a transcript callback reported failure");
+    PK_TRY(whir_prove(P->cw, &cmw, ws, 3, nw));
+    if (dev) {
+        // the one host round trip of the device-transcript flow: header + proof string
+        const size_t bytes = pk::DEVTS_HEADER_BYTES + 4 * std::min(bound_words, NARG_CAP_WORDS);
+        PK_CUDA(ctx, cudaMemcpyAsync(M.pin_narg, M.ts, bytes, cudaMemcpyDeviceToHost, st()));
+    }
+    PK_TRY(sync());
+    if (fs && !fs->ok()) return pk::set_err(ctx, PK_ERR_INVALID_ARG, "prove: a transcript callback reported failure");
     T()[8] += now_s() - t_start;
     T()[7] = T()[8] - (T()[0] + T()[1] + T()[2] + T()[3] + T()[4] + T()[5] + T()[6]);
     return PK_OK;
@@ -702,6 +823,8 @@ pk_prover::~pk_prover() {
     PK_BIND(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(d_interned);
+    cudaFree(mem.dev);
+    if (mem.pin) cudaFreeHost(mem.pin);
     pk_buf_free(ctx, masked_w);
     pk_buf_free(ctx, g_w);
     pk_buf_free(ctx, masked_h);
@@ -741,9 +864,48 @@ int pk_prover_create(pk_ctx* ctx, const pk_r1cs* r1cs, pk_prover** out) {
     PK_TRY(upload_csr(ctx, r1cs->a, &p->A, &p->At));
     PK_TRY(upload_csr(ctx, r1cs->b, &p->B, &p->Bt));
     PK_TRY(upload_csr(ctx, r1cs->c, nullptr, &p->Ct));
+    {   // sponge IV: Keccak tag of the domain separator as a field element (sponge.rs:47-52); 1/2 (utils/mod.rs:23-25)
+        uint8_t tag[32];
+        uint64_t c[4];
+        pkh::domsep_tag(p->domsep, tag);
+        std::memcpy(c, tag, 32);
+        pkh::to_canonical(pkh::from_canonical(c), c);
+        p->iv_canonical = pk::to_arg(c);
+        p->half = pk::to_arg(pkh::half().l);
+    }
+    {   // work areas of the protocol flow: one device allocation, one pinned allocation
+        FlowMem& M = p->mem;
+        const size_t ts_bytes = pk::DEVTS_HEADER_BYTES + 4 * NARG_CAP_WORDS, board_bytes = 32 * BOARD_ELEMS, hint_bytes = 4 * HINT_WORDS;
+        const size_t stir_bytes = 2048, idx_bytes = 8 * pk::OPEN_MAX_QUERIES, misc_bytes = 256;
+        PK_CUDA(ctx, cudaMalloc((void**)&M.dev, ts_bytes + board_bytes + hint_bytes + stir_bytes + idx_bytes + misc_bytes));
+        char* q = M.dev;
+        M.ts = q;
+        q += ts_bytes;
+        M.board = q;
+        q += board_bytes;
+        M.hint = (uint32_t*)q;
+        q += hint_bytes;
+        M.stir_bytes = (uint32_t*)q;
+        q += stir_bytes;
+        M.stir_idx = (uint64_t*)q;
+        q += idx_bytes;
+        M.n_idx = (uint32_t*)q;
+        M.pow = (pk::PowCtrl*)(q + 64);
+        PK_CUDA(ctx, cudaMemset(M.dev, 0, ts_bytes + board_bytes + hint_bytes + stir_bytes + idx_bytes + misc_bytes));
+        PK_CUDA(ctx, cudaMallocHost((void**)&M.pin, PIN_SCALAR_BYTES + hint_bytes + ts_bytes));
+        M.pin_hint = M.pin + PIN_SCALAR_BYTES;
+        M.pin_narg = M.pin_hint + hint_bytes;
+    }
+    p->host_transcript = std::getenv("PK_HOST_TRANSCRIPT") && std::getenv("PK_HOST_TRANSCRIPT")[0] == '1';
     *out = p.release();
     return PK_OK;
 }
+int pk_prover_set_host_transcript(pk_prover* p, int on) {
+    if (!p) return PK_ERR_INVALID_ARG;
+    p->host_transcript = on != 0;
+    return PK_OK;
+}
+uint64_t pk_prover_host_syncs(const pk_prover* p) { return p ? p->host_syncs : 0; }
 void pk_prover_destroy(pk_prover* p) { delete p; }
 // seam: `impl Mul<&[FieldElement]> for HydratedSparseMatrix` and its transposed twin (provekit/common/src/sparse_matrix.rs:
 // 148-184) on the device-resident R1CS: out = M x (x: num_witnesses, out: num_constraints) or out = x^T M (x:
@@ -765,8 +927,12 @@ void pk_prover_shapes(const pk_prover* p, int* m, int* m0, int* mh) {
     if (m0) *m0 = p ? p->m0 : 0;
     if (mh) *mh = p ? p->mh : 0;
 }
-// H2D staging of one proof's inputs: witness (zero-padded) || mask, g, blinding cubics || mask, g
-int pk_prover_upload_inputs(pk_prover* p, const uint64_t* witness, const pk_rand* rnd) {
+}  // extern "C"
+namespace {
+// H2D staging of one proof's inputs: witness (zero-padded) || mask, g, blinding cubics || mask, g.  do_sync: return only
+// when the host arrays may be reused (the stand-alone entry points); inside pk_prove the proof's own final
+// synchronisation covers it
+int upload_inputs(pk_prover* p, const uint64_t* witness, const pk_rand* rnd, bool do_sync) {
     if (!p) return PK_ERR_INVALID_ARG;
     pk_ctx* ctx = p->ctx;
     PK_BIND(ctx);
@@ -791,8 +957,7 @@ int pk_prover_upload_inputs(pk_prover* p, const uint64_t* witness, const pk_rand
     PK_CUDA(ctx, cudaMemcpyAsync(p->masked_h->d, rnd->blind, 4 * (size_t)p->m0 * 32, cudaMemcpyHostToDevice, st));
     PK_CUDA(ctx, cudaMemcpyAsync((char*)p->masked_h->d + halfh * 32, rnd->mask_h, halfh * 32, cudaMemcpyHostToDevice, st));
     PK_CUDA(ctx, cudaMemcpyAsync(p->g_h->d, rnd->g_h, Nh * 32, cudaMemcpyHostToDevice, st));
-    p->blind.assign(reinterpret_cast<const Fr*>(rnd->blind), reinterpret_cast<const Fr*>(rnd->blind) + 4 * (size_t)p->m0);
-    PK_CUDA(ctx, cudaStreamSynchronize(st));
+    if (do_sync) PK_CUDA(ctx, cudaStreamSynchronize(st));
     std::memset(p->timings, 0, sizeof p->timings);
     p->timings[1] = now_s() - t0;  // H2D staging time
     p->timings[8] = p->timings[1];
@@ -801,7 +966,7 @@ int pk_prover_upload_inputs(pk_prover* p, const uint64_t* witness, const pk_rand
 }
 // same staging with the masks drawn ON THE DEVICE from `seed` (pk_rng_fill streams 0..4 = mask_w, g_w, blind, mask_h,
 // g_h): only the witness crosses PCIe.  The reference draws them from thread_rng inside prove (whir_r1cs.rs:211-225).
-int pk_prover_upload_inputs_seeded(pk_prover* p, const uint64_t* witness, const uint8_t seed[32]) {
+int upload_inputs_seeded(pk_prover* p, const uint64_t* witness, const uint8_t seed[32], bool do_sync) {
     if (!p) return PK_ERR_INVALID_ARG;
     pk_ctx* ctx = p->ctx;
     PK_BIND(ctx);
@@ -825,14 +990,18 @@ int pk_prover_upload_inputs_seeded(pk_prover* p, const uint64_t* witness, const 
     PK_TRY(pk_rng_fill(ctx, p->masked_h, 0, nb, seed, 2));
     PK_TRY(pk_rng_fill(ctx, p->masked_h, halfh, halfh, seed, 3));
     PK_TRY(pk_rng_fill(ctx, p->g_h, 0, Nh, seed, 4));
-    p->blind.resize(nb);
-    PK_CUDA(ctx, cudaMemcpyAsync(p->blind.data(), p->masked_h->d, nb * 32, cudaMemcpyDeviceToHost, st));
-    PK_CUDA(ctx, cudaStreamSynchronize(st));
+    if (do_sync) PK_CUDA(ctx, cudaStreamSynchronize(st));
     std::memset(p->timings, 0, sizeof p->timings);
     p->timings[1] = now_s() - t0;
     p->timings[8] = p->timings[1];
     p->staged = true;
     return PK_OK;
+}
+}  // namespace
+extern "C" {
+int pk_prover_upload_inputs(pk_prover* p, const uint64_t* witness, const pk_rand* rnd) { return upload_inputs(p, witness, rnd, true); }
+int pk_prover_upload_inputs_seeded(pk_prover* p, const uint64_t* witness, const uint8_t seed[32]) {
+    return upload_inputs_seeded(p, witness, seed, true);
 }
 int pk_prove_staged(pk_prover* p, uint8_t** out, size_t* out_len) {
     if (!p) return PK_ERR_INVALID_ARG;
@@ -844,15 +1013,32 @@ int pk_prove_staged(pk_prover* p, uint8_t** out, size_t* out_len) {
     std::memset(p->timings, 0, sizeof p->timings);
     p->timings[1] = keep1;
     p->timings[8] = keep1;
-    pkh::ProverState fs(p->domsep);
-    Prover pr(p, fs);
-    PK_TRY(pr.run());
-    std::vector<uint8_t>& narg = fs.narg();
-    uint8_t* buf = (uint8_t*)std::malloc(narg.size() ? narg.size() : 1);
+    const uint8_t* src;
+    size_t len;
+    std::unique_ptr<pkh::ProverState> host_fs;
+    if (p->host_transcript) {  // the in-tree sponge on the host: every challenge is a host round trip
+        host_fs.reset(new pkh::ProverState(p->domsep));
+        Flow fl(p, host_fs.get());
+        PK_TRY(fl.run());
+        src = host_fs->narg().data();
+        len = host_fs->narg().size();
+    } else {  // default: the transcript lives on the device, the proof string arrives with the final synchronisation
+        Flow fl(p, nullptr);
+        PK_TRY(fl.run());
+        uint32_t hdr[24];
+        std::memcpy(hdr, p->mem.pin_narg, sizeof hdr);
+        const uint32_t words = hdr[18], err = hdr[20];  // pk::DevTs: narg_words, error
+        if (err != 0 || words > fl.bound_words)
+            return pk::set_err(ctx, PK_ERR_INTERNAL, "prove: device transcript reported error %u (%u words, bound %zu)", err, words,
+                               fl.bound_words);
+        src = p->mem.pin_narg + pk::DEVTS_HEADER_BYTES;
+        len = 4 * (size_t)words;
+    }
+    uint8_t* buf = (uint8_t*)std::malloc(len ? len : 1);
     if (!buf) return pk::set_err(ctx, PK_ERR_OOM, "prove: host allocation failed");
-    std::memcpy(buf, narg.data(), narg.size());
+    std::memcpy(buf, src, len);
     *out = buf;
-    *out_len = narg.size();
+    *out_len = len;
     return PK_OK;
 }
 int pk_prove_staged_with_transcript(pk_prover* p, const pk_transcript_vtbl* vt, void* user) {
@@ -867,21 +1053,27 @@ int pk_prove_staged_with_transcript(pk_prover* p, const pk_transcript_vtbl* vt, 
     p->timings[1] = keep1;
     p->timings[8] = keep1;
     pkh::CallbackTranscript fs(vt, user);
-    Prover pr(p, fs);
-    return pr.run();
+    Flow fl(p, &fs);
+    return fl.run();
 }
 int pk_prove_with_transcript(pk_prover* p, const uint64_t* witness, const pk_rand* rnd, const pk_transcript_vtbl* vt, void* user) {
-    PK_TRY(pk_prover_upload_inputs(p, witness, rnd));
-    return pk_prove_staged_with_transcript(p, vt, user);
-}
-int pk_prove(pk_prover* p, const uint64_t* witness, const pk_rand* rnd, uint8_t** out, size_t* out_len) {
-    PK_TRY(pk_prover_upload_inputs(p, witness, rnd));
-    int rc = pk_prove_staged(p, out, out_len);
+    PK_TRY(upload_inputs(p, witness, rnd, false));
+    int rc = pk_prove_staged_with_transcript(p, vt, user);
+    if (rc != PK_OK && p && p->ctx && p->ctx->stream) cudaStreamSynchronize(p->ctx->stream);
     return rc;
 }
+// the input uploads are asynchronous: on a failed proof make sure they no longer read the caller's arrays
+static int drain_on_error(pk_prover* p, int rc) {
+    if (rc != PK_OK && p && p->ctx && p->ctx->stream) cudaStreamSynchronize(p->ctx->stream);
+    return rc;
+}
+int pk_prove(pk_prover* p, const uint64_t* witness, const pk_rand* rnd, uint8_t** out, size_t* out_len) {
+    PK_TRY(upload_inputs(p, witness, rnd, false));
+    return drain_on_error(p, pk_prove_staged(p, out, out_len));
+}
 int pk_prove_seeded(pk_prover* p, const uint64_t* witness, const uint8_t seed[32], uint8_t** out, size_t* out_len) {
-    PK_TRY(pk_prover_upload_inputs_seeded(p, witness, seed));
-    return pk_prove_staged(p, out, out_len);
+    PK_TRY(upload_inputs_seeded(p, witness, seed, false));
+    return drain_on_error(p, pk_prove_staged(p, out, out_len));
 }
 void pk_free(void* p) { std::free(p); }
 void pk_prover_timings(const pk_prover* p, double out[9]) {

@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(MERKLE_LEAF_BLOCK) k_merkle_leaves(const fr* _
 }
 // n_in nodes of one tree level (heap positions [n_in, 2 n_in)) -> every block reduces `per_block` (= 2 * blockDim.x) of them
 // through log2(per_block) levels to one node, storing all inner nodes
-__global__ void __launch_bounds__(1024) k_merkle_reduce(fr* nodes, size_t n_in, int per_block) {
+__global__ void __launch_bounds__(1024) k_merkle_reduce(fr* nodes, size_t n_in, int per_block, fr* root_mont_out) {
     extern __shared__ uint4 smem_raw[];
     fr* sd = reinterpret_cast<fr*>(smem_raw);
     const int tid = threadIdx.x;
@@ -474,6 +474,7 @@ __global__ void __launch_bounds__(1024) k_merkle_reduce(fr* nodes, size_t n_in, 
             fr h = sky_compress(a, b);
             sd[tid] = h;
             fr_store(&nodes[lvl + off + tid], h);
+            if (root_mont_out && lvl == 1) fr_store(root_mont_out, fr_to_mont(h));
         }
         __syncthreads();
     }
@@ -487,18 +488,18 @@ int launch_merkle_leaves(cudaStream_t st, const void* leaves, size_t L, size_t w
     return 1;
 }
 // all inner levels: L leaf digests at heap positions [L, 2L) -> root at nodes[1]
-int launch_merkle_upper(cudaStream_t st, size_t L, void* nodes) {
+int launch_merkle_upper(cudaStream_t st, size_t L, void* nodes, void* root_mont_out) {
     int launches = 0;
     size_t n = L;
     while (n > (size_t)MERKLE_TOP_MAX_IN) {
         const int per_block = n > ((size_t)1 << 19) ? 1024 : 256;  // keeps any tree of up to 2^21 leaves at three launches
-        k_merkle_reduce<<<(unsigned)(n / per_block), per_block / 2, (per_block / 2) * sizeof(fr), st>>>((fr*)nodes, n, per_block);
+        k_merkle_reduce<<<(unsigned)(n / per_block), per_block / 2, (per_block / 2) * sizeof(fr), st>>>((fr*)nodes, n, per_block, nullptr);
         n /= per_block;
         launches++;
     }
     if (n >= 2) {
         const int threads = (int)(n / 2) < 32 ? 32 : (int)(n / 2);
-        k_merkle_reduce<<<1, threads, (n / 2) * sizeof(fr), st>>>((fr*)nodes, n, (int)n);
+        k_merkle_reduce<<<1, threads, (n / 2) * sizeof(fr), st>>>((fr*)nodes, n, (int)n, (fr*)root_mont_out);
         launches++;
     }
     return launches;
@@ -510,16 +511,39 @@ int launch_merkle_upper(cudaStream_t st, size_t L, void* nodes) {
 // block (2k + part): part 0 builds the high table of point k (variables [0, nv_hi), scaled), part 1 the low table
 // (variables [nv_hi, nv_hi + nv_lo))
 __global__ void __launch_bounds__(256) k_tensor_tables(const fr* __restrict__ points, int pt_stride, int nv_hi, int nv_lo,
-                                                       const fr* __restrict__ scales, bool eq_mode, fr* out_hi, fr* out_lo) {
+                                                       const fr* __restrict__ scales, bool eq_mode, fr* out_hi, fr* out_lo,
+                                                       TensorSrc src) {
     const size_t k = blockIdx.x >> 1;
     const int part = blockIdx.x & 1;
     const int nv = part ? nv_lo : nv_hi, var_off = part ? nv_hi : 0;
     fr* T = (part ? out_lo : out_hi) + (k << nv);
-    if (threadIdx.x == 0) fr_store(&T[0], (!part && scales) ? fr_load(&scales[k]) : fr_one());
+    const bool live = !src.count || k < (size_t)*src.count;
+    if (threadIdx.x == 0) fr_store(&T[0], !live ? fr_zero() : ((!part && scales) ? fr_load(&scales[k]) : fr_one()));
+    // univariate points: variable j of n = nv_hi + nv_lo is z^(2^(n-1-j)); the loop below walks j downwards, i.e. the
+    // power doubles every step, starting from z^(2^(n - var_off - nv)) (every thread carries the same running power)
+    fr zp = fr_zero();
+    if (src.mode == TENSOR_PTS_UNIVARIATE) {
+        zp = fr_load(&points[k]);
+    } else if (src.mode == TENSOR_PTS_ROOTS) {
+        const uint32_t D = 1u << src.log_d, halfD = D >> 1;
+        uint32_t e = live ? (uint32_t)src.exps[k] & (D - 1) : 0u;
+        const bool neg = halfD && e >= halfD;
+        if (halfD) e &= halfD - 1;
+        zp = e ? fr_load_nc(&reinterpret_cast<const fr*>(src.W)[(size_t)e << src.tbl_shift]) : fr_one();
+        if (neg) zp = fr_neg(zp);
+    }
+    if (src.mode != TENSOR_PTS_EXPLICIT)
+        for (int i = nv_hi + nv_lo - var_off - nv; i > 0; i--) zp = fr_sqr(zp);
     __syncthreads();
     int len = 1;
     for (int j = nv - 1; j >= 0; j--) {  // last variable <-> least significant index bit
-        fr x = fr_load(&points[k * pt_stride + var_off + j]);
+        fr x;
+        if (src.mode == TENSOR_PTS_EXPLICIT) {
+            x = fr_load(&points[k * pt_stride + var_off + j]);
+        } else {
+            x = zp;
+            zp = fr_sqr(zp);
+        }
         for (int i = threadIdx.x; i < len; i += blockDim.x) {
             fr t = fr_load(&T[i]);
             fr s1 = fr_mul(t, x);
@@ -531,10 +555,10 @@ __global__ void __launch_bounds__(256) k_tensor_tables(const fr* __restrict__ po
     }
 }
 int launch_tensor_tables(cudaStream_t st, const void* points, size_t K, int pt_stride, int nv_hi, int nv_lo,
-                         const void* scales, bool eq_mode, void* out_hi, void* out_lo) {
+                         const void* scales, bool eq_mode, void* out_hi, void* out_lo, TensorSrc src) {
     if (K == 0) return 0;
     k_tensor_tables<<<(unsigned)(2 * K), 256, 0, st>>>((const fr*)points, pt_stride, nv_hi, nv_lo, (const fr*)scales, eq_mode,
-                                                     (fr*)out_hi, (fr*)out_lo);
+                                                     (fr*)out_hi, (fr*)out_lo, src);
     return 1;
 }
 __global__ void __launch_bounds__(256) k_tensor_accumulate(fr* out, size_t n, const fr* __restrict__ hi,
@@ -653,19 +677,20 @@ int launch_multi_tensor_dot(cudaStream_t st, const void* const* a, int na, size_
         return -1;
     return 1;
 }
-__global__ void __launch_bounds__(256) k_axpy(fr* y, const fr* __restrict__ x, fr_arg a, size_t n) {
+__global__ void __launch_bounds__(256) k_axpy(fr* y, const fr* __restrict__ x, fr_arg a, const fr* a_ptr, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    fr_store(&y[i], fr_add(fr_load(&y[i]), fr_mul(arg_fr(a), fr_load_nc(&x[i]))));
+    const fr s = a_ptr ? fr_load(a_ptr) : arg_fr(a);
+    fr_store(&y[i], fr_add(fr_load(&y[i]), fr_mul(s, fr_load_nc(&x[i]))));
 }
-int launch_axpy(cudaStream_t st, void* y, const void* x, fr_arg a, size_t n) {
+int launch_axpy(cudaStream_t st, void* y, const void* x, fr_arg a, const void* a_ptr, size_t n) {
     if (n == 0) return 0;
-    k_axpy<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((fr*)y, (const fr*)x, a, n);
+    k_axpy<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((fr*)y, (const fr*)x, a, (const fr*)a_ptr, n);
     return 1;
 }
 // K8: 2^k consecutive coefficients -> multilinear value, r[j] binds bit j (k <= 4)
 __global__ void __launch_bounds__(128) k_fold_coeffs(const fr* __restrict__ c, size_t nout, const fr* __restrict__ r,
-                                                     int k, fr* out) {
+                                                     int r_stride, int k, fr* out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nout) return;
     int w = 1 << k;
@@ -677,7 +702,7 @@ __global__ void __launch_bounds__(128) k_fold_coeffs(const fr* __restrict__ c, s
 #pragma unroll
     for (int v = 0; v < 4; v++) {
         if (v < k) {
-            fr rv = fr_load_nc(&r[v]);
+            fr rv = fr_load(&r[v * r_stride]);
             len >>= 1;
 #pragma unroll
             for (int j = 0; j < 8; j++)
@@ -686,9 +711,9 @@ __global__ void __launch_bounds__(128) k_fold_coeffs(const fr* __restrict__ c, s
     }
     fr_store(&out[i], tmp[0]);
 }
-int launch_fold_coeffs(cudaStream_t st, const void* coeffs, int log_n, const void* r_dev, int k, void* out) {
+int launch_fold_coeffs(cudaStream_t st, const void* coeffs, int log_n, const void* r_dev, int r_stride, int k, void* out) {
     size_t nout = (size_t)1 << (log_n - k);
-    k_fold_coeffs<<<(unsigned)((nout + 127) / 128), 128, 0, st>>>((const fr*)coeffs, nout, (const fr*)r_dev, k, (fr*)out);
+    k_fold_coeffs<<<(unsigned)((nout + 127) / 128), 128, 0, st>>>((const fr*)coeffs, nout, (const fr*)r_dev, r_stride, k, (fr*)out);
     return 1;
 }
 
@@ -701,9 +726,11 @@ int launch_fold_coeffs(cudaStream_t st, const void* coeffs, int log_n, const voi
 // instead of 2^n per point.  Field arithmetic is exact, so the result equals the per-point tensor method bit for bit.
 // ------------------------------------------------------------------------------------------------
 // s[e_k] += scalar_k, serially (k is ~100; duplicates of e_k must add up)
-__global__ void k_scatter_add(fr* s, const uint64_t* __restrict__ exps, const fr* __restrict__ scalars, size_t k) {
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-        for (size_t i = 0; i < k; i++) fr_store(&s[exps[i]], fr_add(fr_load(&s[exps[i]]), fr_load_nc(&scalars[i])));
+__global__ void k_scatter_add(fr* s, const uint64_t* exps, const fr* scalars, size_t k, const uint32_t* k_ptr) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (k_ptr) k = *k_ptr;
+        for (size_t i = 0; i < k; i++) fr_store(&s[exps[i]], fr_add(fr_load(&s[exps[i]]), fr_load(&scalars[i])));
+    }
 }
 // u[j] = sum_{c<16} omega_D^(j c) * lv[(j mod D/16) * 16 + c],  j < n_out  (lv: RS-encode leaf layout, leaf i entry c =
 // f_c((omega_D^16)^i) with f_c the stride-16 sub-polynomials): the last radix-16 step of the size-D transform
@@ -729,9 +756,9 @@ __global__ void __launch_bounds__(256) k_add_inplace(fr* y, const fr* __restrict
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) fr_store(&y[i], fr_add(fr_load(&y[i]), fr_load_nc(&x[i])));
 }
-int launch_scatter_add(cudaStream_t st, void* s, const uint64_t* exps, const void* scalars, size_t k) {
-    if (k == 0) return 0;
-    k_scatter_add<<<1, 32, 0, st>>>((fr*)s, exps, (const fr*)scalars, k);
+int launch_scatter_add(cudaStream_t st, void* s, const uint64_t* exps, const void* scalars, size_t k, const uint32_t* k_ptr) {
+    if (k == 0 && !k_ptr) return 0;
+    k_scatter_add<<<1, 32, 0, st>>>((fr*)s, exps, (const fr*)scalars, k, k_ptr);
     return 1;
 }
 int launch_dft16_combine(cudaStream_t st, const void* lv, void* u, size_t n_out, int log_d, const void* table, int table_log_m) {
@@ -750,11 +777,11 @@ int launch_add_inplace(cudaStream_t st, void* y, const void* x, size_t n) {
 // the map of provekit/prover/src/whir_r1cs.rs:284-291).  MSB pairing: i <-> i + len/2.
 // ------------------------------------------------------------------------------------------------
 template <bool FOLD>
-__global__ void __launch_bounds__(256, 2) k_zk_sumcheck(fr* a, fr* b, fr* c, fr* eq, size_t half, fr_arg foldv, fr* partials,
-                                                     fr* result) {
+__global__ void __launch_bounds__(256, 2) k_zk_sumcheck(fr* a, fr* b, fr* c, fr* eq, size_t half, fr_arg foldv,
+                                                     const fr* fold_ptr, fr* partials, fr* result) {
     // `half` = (length after folding) / 2; before folding the arrays are 4*half long
     fr acc[3] = {fr_zero(), fr_zero(), fr_zero()};
-    fr f = arg_fr(foldv);
+    fr f = fold_ptr ? fr_load(fold_ptr) : arg_fr(foldv);
     // one array at a time, (x0, d = x1 - x0) per array, products formed as soon as their inputs exist: keeps the live set
     // near 90 registers so two 256-thread blocks fit per SM
     auto fetch = [&](fr* x, size_t i, fr& x0, fr& d) {
@@ -789,14 +816,15 @@ __global__ void __launch_bounds__(256, 2) k_zk_sumcheck(fr* a, fr* b, fr* c, fr*
     grid_reduce<3>(acc, partials, result);
 }
 int launch_zk_sumcheck_round(cudaStream_t st, void* a, void* b, void* c, void* eq, int log_n, bool has_fold,
-                             fr_arg fold, void* partials, void* result) {
+                             fr_arg fold, const void* fold_ptr, void* partials, void* result) {
     size_t n_after = (size_t)1 << (has_fold ? log_n - 1 : log_n);
     size_t half = n_after / 2;
     int g = grid_for(half, 256, REDUCE_MAX_BLOCKS);
     if (has_fold)
-        k_zk_sumcheck<true><<<g, 256, 0, st>>>((fr*)a, (fr*)b, (fr*)c, (fr*)eq, half, fold, (fr*)partials, (fr*)result);
+        k_zk_sumcheck<true><<<g, 256, 0, st>>>((fr*)a, (fr*)b, (fr*)c, (fr*)eq, half, fold, (const fr*)fold_ptr, (fr*)partials,
+                                               (fr*)result);
     else
-        k_zk_sumcheck<false><<<g, 256, 0, st>>>((fr*)a, (fr*)b, (fr*)c, (fr*)eq, half, fold, (fr*)partials, (fr*)result);
+        k_zk_sumcheck<false><<<g, 256, 0, st>>>((fr*)a, (fr*)b, (fr*)c, (fr*)eq, half, fold, nullptr, (fr*)partials, (fr*)result);
     return 1;
 }
 
@@ -805,10 +833,10 @@ int launch_zk_sumcheck_round(cudaStream_t st, void* a, void* b, void* c, void* e
 // ------------------------------------------------------------------------------------------------
 template <bool FOLD>
 __global__ void __launch_bounds__(256, 2) k_whir_sumcheck(const fr* __restrict__ p_in, const fr* __restrict__ w_in,
-                                                       fr* p_out, fr* w_out, size_t pairs, fr_arg foldv, fr* partials,
-                                                       fr* result) {
+                                                       fr* p_out, fr* w_out, size_t pairs, fr_arg foldv, const fr* fold_ptr,
+                                                       fr* partials, fr* result) {
     fr acc[3] = {fr_zero(), fr_zero(), fr_zero()};
-    fr f = arg_fr(foldv);
+    fr f = fold_ptr ? fr_load(fold_ptr) : arg_fr(foldv);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (size_t)gridDim.x * blockDim.x) {
         fr p0, p1, w0, w1;
         if (FOLD) {
@@ -835,15 +863,15 @@ __global__ void __launch_bounds__(256, 2) k_whir_sumcheck(const fr* __restrict__
     grid_reduce<3>(acc, partials, result);
 }
 int launch_whir_sumcheck_round(cudaStream_t st, const void* p_in, const void* w_in, void* p_out, void* w_out,
-                               int log_n, bool has_fold, fr_arg fold, void* partials, void* result) {
+                               int log_n, bool has_fold, fr_arg fold, const void* fold_ptr, void* partials, void* result) {
     size_t n_after = (size_t)1 << (has_fold ? log_n - 1 : log_n);
     size_t pairs = n_after / 2;
     int g = grid_for(pairs, 256, REDUCE_MAX_BLOCKS);
     if (has_fold)
         k_whir_sumcheck<true><<<g, 256, 0, st>>>((const fr*)p_in, (const fr*)w_in, (fr*)p_out, (fr*)w_out, pairs, fold,
-                                                 (fr*)partials, (fr*)result);
+                                                 (const fr*)fold_ptr, (fr*)partials, (fr*)result);
     else
-        k_whir_sumcheck<false><<<g, 256, 0, st>>>((const fr*)p_in, (const fr*)w_in, (fr*)p_out, (fr*)w_out, pairs, fold,
+        k_whir_sumcheck<false><<<g, 256, 0, st>>>((const fr*)p_in, (const fr*)w_in, (fr*)p_out, (fr*)w_out, pairs, fold, nullptr,
                                                   (fr*)partials, (fr*)result);
     return 1;
 }

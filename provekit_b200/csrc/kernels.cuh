@@ -24,7 +24,8 @@ int launch_wavelet(cudaStream_t st, void* a, int log_n, bool inverse);
 int launch_wavelet_mode(cudaStream_t st, void* a, int log_n, int mode);
 // pieces of the sparse-DFT eq-weight batch (see kernels.cu): s[exps[i]] += scalars[i];  u = radix-16 recombination of an
 // RS-encode (rate 1) leaf array into the plain size-2^log_d transform, first n_out outputs;  y += x
-int launch_scatter_add(cudaStream_t st, void* s, const uint64_t* exps, const void* scalars, size_t k);
+// k_ptr (device) overrides k when non-null
+int launch_scatter_add(cudaStream_t st, void* s, const uint64_t* exps, const void* scalars, size_t k, const uint32_t* k_ptr = nullptr);
 int launch_dft16_combine(cudaStream_t st, const void* lv, void* u, size_t n_out, int log_d, const void* table, int table_log_m);
 int launch_add_inplace(cudaStream_t st, void* y, const void* x, size_t n);
 
@@ -46,14 +47,28 @@ int launch_rs_encode_cols(cudaStream_t st, const void* coeffs, int log_n, int lo
 // K2 Merkle: leaves Montgomery, nodes canonical heap order
 // canonical: the leaf elements are canonical integers already (no Montgomery conversion before hashing)
 int launch_merkle_leaves(cudaStream_t st, const void* leaves, size_t L, size_t w, void* nodes, bool canonical);
-int launch_merkle_upper(cudaStream_t st, size_t L, void* nodes);
+// root_mont_out (device, optional): the root as a Montgomery-form field element (= MerkleConfig::InnerDigest)
+int launch_merkle_upper(cudaStream_t st, size_t L, void* nodes, void* root_mont_out = nullptr);
 
 // tensor-product tables of K points with nv_hi + nv_lo variables each (point k at points[k*pt_stride ..]):
 //   hi_k[idx] = scale_k * prod_{j < nv_hi} (bit_{nv_hi-1-j}(idx) ? f1 : f0)   over the first nv_hi variables,
 //   lo_k[idx] =           prod over the remaining nv_lo variables;            eq: (f0,f1) = (1-x, x);  pow: (1, x)
 // so that T_k[idx] = hi_k[idx >> nv_lo] * lo_k[idx & mask].  scales may be null (= 1).  One launch builds both.
+// Where the K points come from:
+//   TENSOR_PTS_EXPLICIT  points[k * pt_stride + j], j < nv_hi + nv_lo
+//   TENSOR_PTS_UNIVARIATE  point k = (z^(2^(n-1)), .., z^2, z) with z = points[k]  (expand_from_univariate)
+//   TENSOR_PTS_ROOTS       the same with z = omega_D^(exps[k]), D = 2^log_d, read from the twiddle table W
+// count (device, optional): points k >= *count get scale 0, i.e. contribute nothing (batch size known only on the device)
+enum { TENSOR_PTS_EXPLICIT = 0, TENSOR_PTS_UNIVARIATE = 1, TENSOR_PTS_ROOTS = 2 };
+struct TensorSrc {
+    int mode;
+    const uint64_t* exps;
+    const uint32_t* count;
+    const void* W;
+    int tbl_shift, log_d;
+};
 int launch_tensor_tables(cudaStream_t st, const void* points, size_t K, int pt_stride, int nv_hi, int nv_lo,
-                         const void* scales, bool eq_mode, void* out_hi, void* out_lo);
+                         const void* scales, bool eq_mode, void* out_hi, void* out_lo, TensorSrc src = TensorSrc());
 // out[idx] += sum_k hi_k[idx >> lo_bits] * lo_k[idx & mask]
 int launch_tensor_accumulate(cudaStream_t st, void* out, int log_n, const void* hi, const void* lo, size_t K,
                              int lo_bits);
@@ -67,14 +82,17 @@ int launch_multi_dot(cudaStream_t st, const void* const* a, int na, const void* 
                      void* result);
 int launch_multi_tensor_dot(cudaStream_t st, const void* const* a, int na, size_t n, const void* hi, const void* lo,
                             int lo_bits, void* partials, void* result);
-int launch_axpy(cudaStream_t st, void* y, const void* x, fr_arg a, size_t n);
-int launch_fold_coeffs(cudaStream_t st, const void* coeffs, int log_n, const void* r_dev, int k, void* out);
+// a_ptr (device) overrides the by-value scalar when non-null
+int launch_axpy(cudaStream_t st, void* y, const void* x, fr_arg a, const void* a_ptr, size_t n);
+// r_dev[j * r_stride] binds bit j of the in-block index (stride -1: challenges stored newest-first)
+int launch_fold_coeffs(cudaStream_t st, const void* coeffs, int log_n, const void* r_dev, int r_stride, int k, void* out);
 
 // K5 / K7 sumcheck rounds; result: 3 field elements on device
+// fold_ptr (device, Montgomery) overrides the by-value `fold` when non-null: the challenge may never have left the device
 int launch_zk_sumcheck_round(cudaStream_t st, void* a, void* b, void* c, void* eq, int log_n, bool has_fold,
-                             fr_arg fold, void* partials, void* result);
+                             fr_arg fold, const void* fold_ptr, void* partials, void* result);
 int launch_whir_sumcheck_round(cudaStream_t st, const void* p_in, const void* w_in, void* p_out, void* w_out,
-                               int log_n, bool has_fold, fr_arg fold, void* partials, void* result);
+                               int log_n, bool has_fold, fr_arg fold, const void* fold_ptr, void* partials, void* result);
 
 // Sharded sumchecks: all-gather + field sum of the three partial sums of a round, fused behind the reduction as
 // NVLink peer stores.  Every rank owns a mailbox of SHARD_SLOTS x SHARD_MAX_WORLD cells of 128 B (96 B payload + sequence
@@ -121,6 +139,38 @@ int launch_rng_fill(cudaStream_t st, void* out, size_t n, const uint32_t key[8],
 
 // microbenchmark: chains `iters` dependent Montgomery multiplications per thread; returns launches
 int launch_modmul_bench(cudaStream_t st, void* data, size_t n_threads, int iters, bool square);
+
+// ---- glue.cu: protocol flow on the device (transcript, zk-sumcheck bookkeeping, STIR, hints, PoW) ----
+int launch_ts_init(cudaStream_t st, void* ts, fr_arg iv_canonical, uint32_t cap_words);
+int launch_ts_exchange(cudaStream_t st, void* ts, const void* absorb, int na, bool canonical, void* squeeze, int ns);
+int launch_ts_challenge_bytes(cudaStream_t st, void* ts, uint32_t* out_words, int n_bytes);
+int launch_ts_hint(cudaStream_t st, void* ts, const uint32_t* payload, uint32_t len_words, const uint32_t* len_ptr);
+constexpr size_t DEVTS_HEADER_BYTES = 96;
+struct ZkGlue {
+    const fr* blind;  // 4 * m0 cubic coefficients of the blinding polynomials (Montgomery)
+    fr* suffix;       // m0
+    fr* state;        // [0] rho, [1] saved, [2] prefix, [3] sum_g
+    fr* alpha;        // m0 challenges
+    fr* h3;           // the round kernel's [f(0), f(-1), f(inf)]
+    fr* cf;           // the 4 coefficients sent
+    int m0;
+};
+int launch_zk_init(cudaStream_t st, ZkGlue g, fr_arg half);
+int launch_zk_glue(cudaStream_t st, ZkGlue g, int idx, fr_arg half, void* ts_or_null);
+int launch_powers(cudaStream_t st, void* out, const void* base, int n, int first_exp, const uint32_t* count_ptr);
+int launch_expand_powers(cudaStream_t st, void* out, const void* alpha, int m0, size_t len);
+constexpr int OPEN_MAX_QUERIES = 128;  // queries per round <= protocol security level (128) at rate <= 1/2
+int launch_stir_indices(cudaStream_t st, const uint32_t* bytes_words, int nq, int nb, int folded_log, uint64_t* idx, uint32_t* n_idx);
+int launch_open_hints(cudaStream_t st, const void* leaves, bool leaves_canonical, int w, const void* nodes, size_t L, int depth,
+                      const uint64_t* idx, const uint32_t* n_idx, uint32_t* hint1, uint32_t* hint2, uint32_t* lens);
+int launch_hint_scalars(cudaStream_t st, uint32_t* out, const void* src, int n_groups, int group_len, int estride, int gstride);
+struct PowCtrl {
+    uint32_t challenge[8];
+    unsigned long long ticket, best;
+};
+int launch_pow_begin(cudaStream_t st, void* ts, PowCtrl* c);
+int launch_pow_grind(cudaStream_t st, PowCtrl* c, fr_arg threshold, int blocks);
+int launch_pow_end(cudaStream_t st, void* ts, PowCtrl* c);
 
 constexpr int REDUCE_MAX_BLOCKS = 1184;  // 148 SMs x 8
 constexpr int REDUCE_MAX_SUMS = 6;       // field sums per reduction kernel

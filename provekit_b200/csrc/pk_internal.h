@@ -55,6 +55,7 @@ struct pk_commitment {
     void* nodes = nullptr;   // 2L field elements, canonical digests, heap order
     size_t L = 0, w = 0;
     int depth = 0;
+    bool canonical_leaves = false;  // leaves hold canonical integers instead of Montgomery-form elements
 };
 
 namespace pk {
@@ -93,6 +94,17 @@ int ensure_tables(pk_ctx* ctx, size_t elems);
 int ensure_small(pk_ctx* ctx, size_t bytes);
 int ensure_stage(pk_ctx* ctx, size_t bytes);
 cudaError_t init_kernel_attributes();
+// device-pointer forms of the C-ABI helpers (pkwhir.cu): scalars, points and results stay on the device
+int commit_batch_dev(pk_ctx* ctx, const void* const* coeffs, int batch, int log_n, int log_inv_rate, pk_commitment** out,
+                     void* root_mont_dev);
+int dev_eval_univariate(pk_ctx* ctx, const void* const* polys, int k, size_t n, const void* z_dev, void* out_dev);
+int dev_eval_eq(pk_ctx* ctx, const void* point_dev, int mode, int n, const void* scale_dev, void* out);
+int dev_mle_eval_prefix(pk_ctx* ctx, const void* const* evals, int k, int log_n, size_t n_prefix, const void* point_dev,
+                        void* out_dev);
+int dev_eval_eq_roots(pk_ctx* ctx, const uint64_t* exps_dev, const uint32_t* count_dev, size_t kmax, int log_d, int n,
+                      const void* scalars_dev, void* out);
+// skyscraper/core/src/pow.rs:61-82 threshold for `bits` of difficulty (incl. PROVER_BIAS), canonical limbs
+void pow_threshold(double bits, uint64_t out[4]);
 inline fr_arg to_arg(const uint64_t x[4]) {
     fr_arg a;
     for (int i = 0; i < 4; i++) {

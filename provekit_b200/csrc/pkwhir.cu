@@ -315,6 +315,12 @@ static void f64_to_u256(double f, uint64_t out[4]) {
         if (sh != 0 && limb < 3) out[limb + 1] = sig >> (64 - sh);
     }
 }
+}  // extern "C"
+void pk::pow_threshold(double bits, uint64_t out[4]) {
+    double modulus = (double)pkh::P[3] * std::ldexp(1.0, 192);  // pow.rs:19
+    f64_to_u256(std::exp2(-(bits + 0.01)) * modulus, out);      // PROVER_BIAS, pow.rs:6,37
+}
+extern "C" {
 int pk_pow_solve(pk_ctx* ctx, const uint64_t challenge[4], double bits, uint64_t* nonce) {
     PK_BIND(ctx);
     PK_CHECK(ctx, ctx && challenge && nonce, "pow_solve: null argument");
@@ -325,8 +331,7 @@ int pk_pow_solve(pk_ctx* ctx, const uint64_t challenge[4], double bits, uint64_t
         return PK_OK;
     }
     uint64_t thr[4];
-    double modulus = (double)pkh::P[3] * std::ldexp(1.0, 192);  // pow.rs:19
-    f64_to_u256(std::exp2(-(bits + 0.01)) * modulus, thr);      // PROVER_BIAS, pow.rs:6,37
+    pk::pow_threshold(bits, thr);
     unsigned long long init = ~0ULL;
     PK_CUDA(ctx, cudaMemcpyAsync(ctx->d_best, &init, 8, cudaMemcpyHostToDevice, ctx->stream));
     // one launch covers ~8x the expected nonce (miss probability e^-8); blocks above the first hit exit immediately and
@@ -446,12 +451,12 @@ int pk_merkle_build(pk_ctx* ctx, const pk_buf* leaves, size_t L, size_t w, pk_bu
     PK_CUDA(ctx, cudaGetLastError());
     return PK_OK;
 }
-int pk_commit_batch(pk_ctx* ctx, const pk_buf* const* coeffs, int batch, int log_n, int log_inv_rate, int fold,
-                    pk_commitment** out, uint64_t root_out[4]) {
-    PK_BIND(ctx);
-    PK_CHECK(ctx, ctx && coeffs && out && root_out && batch >= 1, "commit_batch: bad arguments");
-    PK_CHECK(ctx, fold == 4 && log_n >= fold && log_n + log_inv_rate - fold >= 1, "commit_batch: bad sizes");
-    for (int b = 0; b < batch; b++) PK_CHECK(ctx, coeffs[b] && coeffs[b]->n >= ((size_t)1 << log_n), "commit_batch: poly %d too small", b);
+}  // extern "C"
+namespace pk {
+// commit_batch without a host round trip: the root is left on the device, in Montgomery form, at root_mont_dev
+int commit_batch_dev(pk_ctx* ctx, const void* const* coeffs, int batch, int log_n, int log_inv_rate, pk_commitment** out,
+                     void* root_mont_dev) {
+    const int fold = 4;
     pk_commitment* c = new pk_commitment();
     c->w = ((size_t)batch) << fold;
     c->L = (size_t)1 << (log_n + log_inv_rate - fold);
@@ -462,7 +467,7 @@ int pk_commit_batch(pk_ctx* ctx, const pk_buf* const* coeffs, int batch, int log
         return set_err(ctx, PK_ERR_OOM, "commit_batch: out of device memory");
     }
     for (int b = 0; b < batch; b++) {
-        int rc = rs_encode_raw(ctx, coeffs[b]->d, log_n, log_inv_rate, fold, c->leaves, c->w, (size_t)b << fold);
+        int rc = rs_encode_raw(ctx, coeffs[b], log_n, log_inv_rate, fold, c->leaves, c->w, (size_t)b << fold);
         if (rc != PK_OK) {
             pk_commit_free(ctx, c);
             return rc;
@@ -470,21 +475,39 @@ int pk_commit_batch(pk_ctx* ctx, const pk_buf* const* coeffs, int batch, int log
     }
     {
         ProfScope ps(ctx, PROF_MERKLE_LEAVES);
-        ctx->launches += launch_merkle_leaves(ctx->stream, c->leaves, c->L, c->w, c->nodes, false);
+        ctx->launches += launch_merkle_leaves(ctx->stream, c->leaves, c->L, c->w, c->nodes, c->canonical_leaves);
     }
     {
         ProfScope ps(ctx, PROF_MERKLE_UPPER);
-        ctx->launches += launch_merkle_upper(ctx->stream, c->L, c->nodes);
+        ctx->launches += launch_merkle_upper(ctx->stream, c->L, c->nodes, root_mont_dev);
     }
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_result, (char*)c->nodes + 32, 32, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         pk_commit_free(ctx, c);
         return set_err(ctx, PK_ERR_CUDA, "commit_batch: %s", cudaGetErrorString(e));
     }
-    pkh::Fr root = pkh::from_canonical(ctx->h_result);
-    std::memcpy(root_out, root.l, 32);
+    *out = c;
+    return PK_OK;
+}
+}  // namespace pk
+extern "C" {
+int pk_commit_batch(pk_ctx* ctx, const pk_buf* const* coeffs, int batch, int log_n, int log_inv_rate, int fold,
+                    pk_commitment** out, uint64_t root_out[4]) {
+    PK_BIND(ctx);
+    PK_CHECK(ctx, ctx && coeffs && out && root_out && batch >= 1 && batch <= 8, "commit_batch: bad arguments");
+    PK_CHECK(ctx, fold == 4 && log_n >= fold && log_n + log_inv_rate - fold >= 1, "commit_batch: bad sizes");
+    const void* ptrs[8];
+    for (int b = 0; b < batch; b++) {
+        PK_CHECK(ctx, coeffs[b] && coeffs[b]->n >= ((size_t)1 << log_n), "commit_batch: poly %d too small", b);
+        ptrs[b] = coeffs[b]->d;
+    }
+    pk_commitment* c = nullptr;
+    PK_TRY(commit_batch_dev(ctx, ptrs, batch, log_n, log_inv_rate, &c, ctx->d_result));
+    int rc = fetch_result(ctx, root_out, 1);
+    if (rc != PK_OK) {
+        pk_commit_free(ctx, c);
+        return rc;
+    }
     *out = c;
     return PK_OK;
 }
@@ -551,20 +574,124 @@ int pk_commit_open(pk_ctx* ctx, const pk_commitment* c, const uint64_t* sorted_i
 }
 
 // ---- univariate / multilinear helpers ------------------------------------------------------------
+// The dev_* forms take every scalar, point and count as a DEVICE pointer and leave their result on the device: the
+// protocol flow (host/flow.cpp) chains them without a host round trip.  The C-ABI entry points stage their host
+// arguments into ctx->d_small and call the same code.
+}  // extern "C"
+namespace pk {
 static int split_bits(int n) { return n / 2; }  // low-table bits
 
-// tables for (hi, lo) halves of `point` (nv variables) into ctx->d_tables; returns pointers and the split
-static int build_point_tables(pk_ctx* ctx, const uint64_t* point, int nv, bool eq_mode, char** t_hi, char** t_lo, int* lo_bits) {
+// stages `bytes` of host data into ctx->d_small at `off` (the caller sized d_small); pageable source: ordered by the stream
+static int stage_small(pk_ctx* ctx, size_t off, const void* host, size_t bytes) {
+    if (bytes) PK_CUDA(ctx, cudaMemcpyAsync((char*)ctx->d_small + off, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return PK_OK;
+}
+// (hi, lo) tensor tables of ONE point with nv variables into ctx->d_tables
+static int point_tables(pk_ctx* ctx, const void* point_dev, int mode, int nv, bool eq_mode, const void* scale_dev, char** t_hi,
+                        char** t_lo, int* lo_bits) {
     int lo = split_bits(nv), hi = nv - lo;
-    PK_TRY(ensure_small(ctx, (size_t)(nv + 1) * 32));
     PK_TRY(ensure_tables(ctx, ((size_t)1 << lo) + ((size_t)1 << hi)));
-    if (nv > 0) PK_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, point, (size_t)nv * 32, cudaMemcpyHostToDevice, ctx->stream));
     *t_hi = (char*)ctx->d_tables;
     *t_lo = *t_hi + ((size_t)32 << hi);
     *lo_bits = lo;
-    ctx->launches += launch_tensor_tables(ctx->stream, ctx->d_small, 1, nv, hi, lo, nullptr, eq_mode, *t_hi, *t_lo);
+    TensorSrc src = {};
+    src.mode = mode;
+    ctx->launches += launch_tensor_tables(ctx->stream, point_dev, 1, nv, hi, lo, scale_dev, eq_mode, *t_hi, *t_lo, src);
     return PK_OK;
 }
+int dev_eval_univariate(pk_ctx* ctx, const void* const* polys, int k, size_t n, const void* z_dev, void* out_dev) {
+    int nv = 0;
+    while (((size_t)1 << nv) < n) nv++;
+    char *t_hi, *t_lo;
+    int lo;
+    // point (z^(2^(nv-1)), ..., z^2, z): power tables instead of eq tables
+    ProfScope ps(ctx, PROF_OTHER);
+    PK_TRY(point_tables(ctx, z_dev, TENSOR_PTS_UNIVARIATE, nv, false, nullptr, &t_hi, &t_lo, &lo));
+    int rc = launch_multi_tensor_dot(ctx->stream, polys, k, n, t_hi, t_lo, lo, ctx->d_partials, out_dev);
+    if (rc < 0) return set_err(ctx, PK_ERR_INVALID_ARG, "eval_univariate: unsupported batch size %d", k);
+    ctx->launches += rc;
+    PK_CUDA(ctx, cudaGetLastError());
+    return PK_OK;
+}
+// out[x] += scale * eq(point, x) over n variables; mode: explicit point (n elements) or univariate z (one element)
+int dev_eval_eq(pk_ctx* ctx, const void* point_dev, int mode, int n, const void* scale_dev, void* out) {
+    char *t_hi, *t_lo;
+    int lo;
+    ProfScope ps(ctx, PROF_OTHER);
+    PK_TRY(point_tables(ctx, point_dev, mode, n, true, scale_dev, &t_hi, &t_lo, &lo));
+    ctx->launches += launch_tensor_accumulate(ctx->stream, out, n, t_hi, t_lo, 1, lo);
+    PK_CUDA(ctx, cudaGetLastError());
+    return PK_OK;
+}
+int dev_mle_eval_prefix(pk_ctx* ctx, const void* const* evals, int k, int log_n, size_t n_prefix, const void* point_dev,
+                        void* out_dev) {
+    char *t_hi, *t_lo;
+    int lo;
+    ProfScope ps(ctx, PROF_OTHER);
+    PK_TRY(point_tables(ctx, point_dev, TENSOR_PTS_EXPLICIT, log_n, true, nullptr, &t_hi, &t_lo, &lo));
+    int rc = launch_multi_tensor_dot(ctx->stream, evals, k, n_prefix, t_hi, t_lo, lo, ctx->d_partials, out_dev);
+    if (rc < 0) return set_err(ctx, PK_ERR_INVALID_ARG, "mle_eval: unsupported batch size %d", k);
+    ctx->launches += rc;
+    PK_CUDA(ctx, cudaGetLastError());
+    return PK_OK;
+}
+// out[x] += sum_{k < count} scalars[k] * eq(pow(omega_D^(exps[k])), x); kmax bounds the batch (grid sizes, method choice),
+// count_dev (device, may be null = kmax) is the actual size.  See kernels.cu "eq weights of many UNIVARIATE points".
+int dev_eval_eq_roots(pk_ctx* ctx, const uint64_t* exps_dev, const uint32_t* count_dev, size_t kmax, int log_d, int n,
+                      const void* scalars_dev, void* out) {
+    if (kmax == 0) return PK_OK;
+    const size_t N = (size_t)1 << n, D = (size_t)1 << log_d;
+    PK_TRY(ensure_twiddles(ctx, log_d));
+    // the transform costs ~ (D/2)(log D - 4) + 15 * 2^n multiplications, the direct method k * 2^n
+    const bool use_dft = n >= 12 && n <= log_d && log_d >= 8 && (double)kmax * (double)N > 2.0 * (0.5 * D * (log_d - 4) + 16.0 * N);
+    if (!use_dft) {
+        int lo = split_bits(n), hi = n - lo;
+        PK_TRY(ensure_tables(ctx, kmax * (((size_t)1 << lo) + ((size_t)1 << hi))));
+        char* t_hi = (char*)ctx->d_tables;
+        char* t_lo = t_hi + kmax * ((size_t)32 << hi);
+        TensorSrc src = {};
+        src.mode = TENSOR_PTS_ROOTS;
+        src.exps = exps_dev;
+        src.count = count_dev;
+        src.W = ctx->d_twiddles;
+        src.tbl_shift = ctx->twiddle_log_m - log_d;
+        src.log_d = log_d;
+        ProfScope ps(ctx, PROF_OTHER);
+        ctx->launches += launch_tensor_tables(ctx->stream, nullptr, kmax, n, hi, lo, scalars_dev, true, t_hi, t_lo, src);
+        ctx->launches += launch_tensor_accumulate(ctx->stream, out, n, t_hi, t_lo, kmax, lo);
+        PK_CUDA(ctx, cudaGetLastError());
+        return PK_OK;
+    }
+    void *sparse = nullptr, *lv = nullptr;
+    if (cudaMallocAsync(&sparse, D * 32, ctx->stream) != cudaSuccess || cudaMallocAsync(&lv, D * 32, ctx->stream) != cudaSuccess) {
+        if (sparse) cudaFreeAsync(sparse, ctx->stream);
+        return set_err(ctx, PK_ERR_OOM, "eval_eq_roots: out of device memory");
+    }
+    int rc = PK_OK;
+    do {
+        if (cudaMemsetAsync(sparse, 0, D * 32, ctx->stream) != cudaSuccess) {
+            rc = set_err(ctx, PK_ERR_CUDA, "eval_eq_roots: staging failed");
+            break;
+        }
+        {
+            ProfScope ps(ctx, PROF_OTHER);
+            ctx->launches += launch_scatter_add(ctx->stream, sparse, exps_dev, scalars_dev, kmax, count_dev);
+        }
+        if ((rc = rs_encode_raw(ctx, sparse, log_d, 0, 4, lv, 16, 0)) != PK_OK) break;
+        // u overwrites the (consumed) sparse vector, then M^T in place, then out += u
+        ProfScope ps(ctx, PROF_OTHER);
+        ctx->launches += launch_dft16_combine(ctx->stream, lv, sparse, N, log_d, ctx->d_twiddles, ctx->twiddle_log_m);
+        ctx->launches += launch_wavelet_mode(ctx->stream, sparse, n, 2);
+        ctx->launches += launch_add_inplace(ctx->stream, out, sparse, N);
+        if (cudaGetLastError() != cudaSuccess) rc = set_err(ctx, PK_ERR_CUDA, "eval_eq_roots: launch failed");
+    } while (0);
+    cudaFreeAsync(sparse, ctx->stream);
+    cudaFreeAsync(lv, ctx->stream);
+    return rc;
+}
+}  // namespace pk
+extern "C" {
+
 int pk_eval_univariate_batch(pk_ctx* ctx, const pk_buf* const* coeffs, int k, size_t n, const uint64_t z[4], uint64_t* out) {
     PK_BIND(ctx);
     PK_CHECK(ctx, coeffs && z && out && k >= 1 && k <= 3 && n >= 1 && (n & (n - 1)) == 0, "eval_univariate: bad arguments");
@@ -573,21 +700,10 @@ int pk_eval_univariate_batch(pk_ctx* ctx, const pk_buf* const* coeffs, int k, si
         PK_CHECK(ctx, coeffs[j] && coeffs[j]->n >= n, "eval_univariate: polynomial %d too small", j);
         ptrs[j] = coeffs[j]->d;
     }
-    int nv = 0;
-    while (((size_t)1 << nv) < n) nv++;
-    // point (z^(2^(nv-1)), ..., z^2, z): power tables instead of eq tables
-    std::vector<pkh::Fr> pt(nv > 0 ? nv : 1);
-    pkh::Fr acc;
-    std::memcpy(acc.l, z, 32);
-    for (int i = 0; i < nv; i++) {
-        pt[nv - 1 - i] = acc;
-        acc = pkh::sqr(acc);
-    }
-    char *t_hi, *t_lo;
-    int lo;
-    PK_TRY(build_point_tables(ctx, pt[0].l, nv, false, &t_hi, &t_lo, &lo));
-    ctx->launches += launch_multi_tensor_dot(ctx->stream, ptrs, k, n, t_hi, t_lo, lo, ctx->d_partials, ctx->d_result);
-    return fetch_result(ctx, out, k);  // also orders the pageable `pt` upload before we return
+    PK_TRY(ensure_small(ctx, 64));
+    PK_TRY(stage_small(ctx, 0, z, 32));
+    PK_TRY(dev_eval_univariate(ctx, ptrs, k, n, ctx->d_small, ctx->d_result));
+    return fetch_result(ctx, out, k);  // also orders the pageable upload before we return
 }
 int pk_eval_univariate(pk_ctx* ctx, const pk_buf* coeffs, size_t n, const uint64_t z[4], uint64_t out[4]) {
     PK_BIND(ctx);
@@ -596,7 +712,8 @@ int pk_eval_univariate(pk_ctx* ctx, const pk_buf* coeffs, size_t n, const uint64
 int pk_axpy(pk_ctx* ctx, pk_buf* y, const pk_buf* x, const uint64_t a[4], size_t n) {
     PK_BIND(ctx);
     PK_CHECK(ctx, y && x && a && y->n >= n && x->n >= n, "axpy: buffer too small");
-    ctx->launches += launch_axpy(ctx->stream, y->d, x->d, to_arg(a), n);
+    ProfScope ps(ctx, PROF_OTHER);
+    ctx->launches += launch_axpy(ctx->stream, y->d, x->d, to_arg(a), nullptr, n);
     PK_CUDA(ctx, cudaGetLastError());
     return PK_OK;
 }
@@ -631,68 +748,31 @@ int pk_eval_eq_batch(pk_ctx* ctx, const uint64_t* points, size_t k, int n, const
     PK_TRY(ensure_tables(ctx, k * (((size_t)1 << lo) + ((size_t)1 << hi))));
     char* d_pts = (char*)ctx->d_small;
     char* d_sc = d_pts + pts_bytes;
-    if (n > 0) PK_CUDA(ctx, cudaMemcpyAsync(d_pts, points, k * (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    PK_CUDA(ctx, cudaMemcpyAsync(d_sc, scalars, sc_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (n > 0) PK_TRY(stage_small(ctx, 0, points, k * (size_t)n * 32));
+    PK_TRY(stage_small(ctx, pts_bytes, scalars, sc_bytes));
     char* t_hi = (char*)ctx->d_tables;
     char* t_lo = t_hi + k * ((size_t)32 << hi);
-    ctx->launches += launch_tensor_tables(ctx->stream, d_pts, k, n, hi, lo, d_sc, true, t_hi, t_lo);
-    ctx->launches += launch_tensor_accumulate(ctx->stream, out->d, n, t_hi, t_lo, k, lo);
+    {
+        ProfScope ps(ctx, PROF_OTHER);
+        ctx->launches += launch_tensor_tables(ctx->stream, d_pts, k, n, hi, lo, d_sc, true, t_hi, t_lo);
+        ctx->launches += launch_tensor_accumulate(ctx->stream, out->d, n, t_hi, t_lo, k, lo);
+    }
     PK_CUDA(ctx, cudaGetLastError());
     // the host arrays may be reused by the caller right away
     PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PK_OK;
 }
-// out[x] += sum_k scalars[k] * eq(pow(z_k), x),  z_k = omega_D^(exps[k]), D = 2^log_d  (see kernels.cu, "eq weights of many
-// univariate points").  Small batches fall back to the per-point tensor method on the expanded points.
 int pk_eval_eq_roots_batch(pk_ctx* ctx, const uint64_t* exps, size_t k, int log_d, int n, const uint64_t* scalars, pk_buf* out) {
     PK_BIND(ctx);
     PK_CHECK(ctx, exps && scalars && out && n >= 0 && n < 40 && log_d >= 0 && log_d <= 28 && out->n >= ((size_t)1 << n),
              "eval_eq_roots: bad arguments");
     if (k == 0) return PK_OK;
     for (size_t i = 0; i < k; i++) PK_CHECK(ctx, exps[i] < ((uint64_t)1 << log_d), "eval_eq_roots: exponent %zu outside the domain", i);
-    const size_t N = (size_t)1 << n, D = (size_t)1 << log_d;
-    // the transform costs ~ (D/2)(log D - 4) + 15 * 2^n multiplications, the direct method k * 2^n
-    const bool use_dft = n >= 12 && n <= log_d && log_d >= 8 && (double)k * (double)N > 2.0 * (0.5 * D * (log_d - 4) + 16.0 * N);
-    if (!use_dft) {
-        std::vector<uint64_t> pts(k * (size_t)(n > 0 ? n : 1) * 4);
-        pkh::Fr g = pkh::root_of_unity(log_d);
-        for (size_t i = 0; i < k; i++) {
-            pkh::Fr z = pkh::pow_u64(g, exps[i]);
-            for (int v = 0; v < n; v++) {  // expand_from_univariate: point[n-1-v] = z^(2^v)
-                std::memcpy(&pts[(i * n + (n - 1 - v)) * 4], z.l, 32);
-                z = pkh::sqr(z);
-            }
-        }
-        return pk_eval_eq_batch(ctx, pts.data(), k, n, scalars, out);
-    }
-    PK_TRY(ensure_twiddles(ctx, log_d));
     PK_TRY(ensure_small(ctx, k * 8 + k * 32));
-    char* d_sc = (char*)ctx->d_small;  // 32-byte elements first: they are read with 128-bit loads
-    uint64_t* d_exps = (uint64_t*)((char*)ctx->d_small + k * 32);
-    void *sparse = nullptr, *lv = nullptr;
-    if (cudaMallocAsync(&sparse, D * 32, ctx->stream) != cudaSuccess || cudaMallocAsync(&lv, D * 32, ctx->stream) != cudaSuccess) {
-        if (sparse) cudaFreeAsync(sparse, ctx->stream);
-        return set_err(ctx, PK_ERR_OOM, "eval_eq_roots: out of device memory");
-    }
-    int rc = PK_OK;
-    do {
-        if (cudaMemcpyAsync(d_exps, exps, k * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
-            cudaMemcpyAsync(d_sc, scalars, k * 32, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
-            cudaMemsetAsync(sparse, 0, D * 32, ctx->stream) != cudaSuccess) {
-            rc = set_err(ctx, PK_ERR_CUDA, "eval_eq_roots: staging failed");
-            break;
-        }
-        ctx->launches += launch_scatter_add(ctx->stream, sparse, d_exps, d_sc, k);
-        if ((rc = rs_encode_raw(ctx, sparse, log_d, 0, 4, lv, 16, 0)) != PK_OK) break;
-        // u overwrites the (consumed) sparse vector, then M^T in place, then out += u
-        ctx->launches += launch_dft16_combine(ctx->stream, lv, sparse, N, log_d, ctx->d_twiddles, ctx->twiddle_log_m);
-        ctx->launches += launch_wavelet_mode(ctx->stream, sparse, n, 2);
-        ctx->launches += launch_add_inplace(ctx->stream, out->d, sparse, N);
-        if (cudaGetLastError() != cudaSuccess) rc = set_err(ctx, PK_ERR_CUDA, "eval_eq_roots: launch failed");
-    } while (0);
-    cudaFreeAsync(sparse, ctx->stream);
-    cudaFreeAsync(lv, ctx->stream);
-    if (rc != PK_OK) return rc;
+    // 32-byte elements first: they are read with 128-bit loads
+    PK_TRY(stage_small(ctx, 0, scalars, k * 32));
+    PK_TRY(stage_small(ctx, k * 32, exps, k * 8));
+    PK_TRY(dev_eval_eq_roots(ctx, (const uint64_t*)((char*)ctx->d_small + k * 32), nullptr, k, log_d, n, ctx->d_small, out->d));
     PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host arrays may be reused by the caller right away
     return PK_OK;
 }
@@ -713,10 +793,9 @@ int pk_mle_eval_batch_prefix(pk_ctx* ctx, const pk_buf* const* evals, int k, int
         PK_CHECK(ctx, evals[j] && evals[j]->n >= ((size_t)1 << log_n), "mle_eval: array %d too small", j);
         ptrs[j] = evals[j]->d;
     }
-    char *t_hi, *t_lo;
-    int lo;
-    PK_TRY(build_point_tables(ctx, point, log_n, true, &t_hi, &t_lo, &lo));
-    ctx->launches += launch_multi_tensor_dot(ctx->stream, ptrs, k, n_prefix, t_hi, t_lo, lo, ctx->d_partials, ctx->d_result);
+    PK_TRY(ensure_small(ctx, (size_t)(log_n + 1) * 32));
+    PK_TRY(stage_small(ctx, 0, point, (size_t)log_n * 32));
+    PK_TRY(dev_mle_eval_prefix(ctx, ptrs, k, log_n, n_prefix, ctx->d_small, ctx->d_result));
     return fetch_result(ctx, out, k);
 }
 int pk_mle_eval(pk_ctx* ctx, const pk_buf* evals, int log_n, const uint64_t* point, uint64_t out[4]) {
@@ -728,8 +807,11 @@ int pk_fold_coeffs(pk_ctx* ctx, const pk_buf* coeffs, int log_n, const uint64_t*
     PK_CHECK(ctx, coeffs && r && out && k >= 0 && k <= 4 && log_n >= k && log_n < 40, "fold_coeffs: bad arguments");
     PK_CHECK(ctx, coeffs->n >= ((size_t)1 << log_n) && out->n >= ((size_t)1 << (log_n - k)), "fold_coeffs: buffer too small");
     PK_TRY(ensure_small(ctx, 4 * 32));
-    if (k > 0) PK_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, r, (size_t)k * 32, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->launches += launch_fold_coeffs(ctx->stream, coeffs->d, log_n, ctx->d_small, k, out->d);
+    if (k > 0) PK_TRY(stage_small(ctx, 0, r, (size_t)k * 32));
+    {
+        ProfScope ps(ctx, PROF_OTHER);
+        ctx->launches += launch_fold_coeffs(ctx->stream, coeffs->d, log_n, ctx->d_small, 1, k, out->d);
+    }
     PK_CUDA(ctx, cudaGetLastError());
     PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PK_OK;
@@ -748,8 +830,8 @@ int pk_zk_sumcheck_round(pk_ctx* ctx, pk_buf* a, pk_buf* b, pk_buf* c, pk_buf* e
     if (fold) f = to_arg(fold);
     {
         ProfScope ps(ctx, PROF_ZK_SUMCHECK);
-        ctx->launches += launch_zk_sumcheck_round(ctx->stream, a->d, b->d, c->d, eq->d, log_n, fold != nullptr, f, ctx->d_partials,
-                                                  ctx->d_result);
+        ctx->launches += launch_zk_sumcheck_round(ctx->stream, a->d, b->d, c->d, eq->d, log_n, fold != nullptr, f, nullptr,
+                                                  ctx->d_partials, ctx->d_result);
     }
     return fetch_result(ctx, out3, 3);
 }
@@ -769,7 +851,8 @@ int pk_whir_sumcheck_round(pk_ctx* ctx, const pk_buf* p_in, const pk_buf* w_in, 
     {
         ProfScope ps(ctx, PROF_WHIR_SUMCHECK);
         ctx->launches += launch_whir_sumcheck_round(ctx->stream, p_in->d, w_in->d, fold ? p_out->d : nullptr,
-                                                    fold ? w_out->d : nullptr, log_n, fold != nullptr, f, ctx->d_partials, ctx->d_result);
+                                                    fold ? w_out->d : nullptr, log_n, fold != nullptr, f, nullptr, ctx->d_partials,
+                                                    ctx->d_result);
     }
     return fetch_result(ctx, out3, 3);
 }
@@ -833,8 +916,8 @@ int pk_zk_sumcheck_round_sharded(pk_ctx* ctx, pk_buf* a, pk_buf* b, pk_buf* c, p
     fr_arg f = {};
     if (fold) f = to_arg(fold);
     ProfScope ps(ctx, PROF_ZK_SUMCHECK);
-    ctx->launches += launch_zk_sumcheck_round(ctx->stream, a->d, b->d, c->d, eq->d, log_n, fold != nullptr, f, ctx->d_partials,
-                                              ctx->d_result);
+    ctx->launches += launch_zk_sumcheck_round(ctx->stream, a->d, b->d, c->d, eq->d, log_n, fold != nullptr, f, nullptr,
+                                              ctx->d_partials, ctx->d_result);
     return exchange_and_fetch(ctx, out3);
 }
 int pk_whir_sumcheck_round_sharded(pk_ctx* ctx, const pk_buf* p_in, const pk_buf* w_in, pk_buf* p_out, pk_buf* w_out, int log_n,
@@ -852,7 +935,7 @@ int pk_whir_sumcheck_round_sharded(pk_ctx* ctx, const pk_buf* p_in, const pk_buf
     }
     ProfScope ps(ctx, PROF_WHIR_SUMCHECK);
     ctx->launches += launch_whir_sumcheck_round(ctx->stream, p_in->d, w_in->d, fold ? p_out->d : nullptr, fold ? w_out->d : nullptr,
-                                                log_n, fold != nullptr, f, ctx->d_partials, ctx->d_result);
+                                                log_n, fold != nullptr, f, nullptr, ctx->d_partials, ctx->d_result);
     return exchange_and_fetch(ctx, out3);
 }
 

@@ -79,6 +79,9 @@ def test_full_size_proof(ctx, orc, which):
     seed = bytes((3 * i + m) & 0xFF for i in range(32))
     pr = pk.Prover(ctx, r)
     proof = pr.prove_seeded(r["witness"], seed)
+    assert pr.host_syncs <= 25, pr.host_syncs  # device transcript: no per-challenge round trips (was ~120)
+    pr.set_host_transcript(True)
+    assert pr.prove_seeded(r["witness"], seed) == proof
     pr.close()
     masks = [np.zeros((k, 4), np.uint64) for k in (1 << (m - 1), 1 << m, 4 * m0, 1 << (mh - 1), 1 << mh)]
     orc.orc_rng_masks(seed, m, m0, mh, *[a.ctypes.data_as(ctypes.c_void_p) for a in masks])

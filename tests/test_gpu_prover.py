@@ -37,10 +37,15 @@ def test_gpu_proof_is_byte_identical_to_oracle(ctx, orc, nc, nfree):
     r = SyntheticR1CS(nc, nfree, seed=nc)
     expected = oracle_prove(orc, r)
     pr = pk.Prover(ctx, as_dict(r))
-    got = pr.prove(r.witness, r.randomness())
+    got = pr.prove(r.witness, r.randomness())          # default: the transcript lives on the device
     assert len(got) == len(expected), (len(got), len(expected))
     assert first_diff(got, expected) == -1
     assert oracle_verify(orc, r, got) == 0
+    assert pr.host_syncs <= 2, pr.host_syncs             # the host only waits for the finished proof string
+    pr.set_host_transcript(True)                         # the same sponge on the host: a round trip per challenge
+    assert pr.prove(r.witness, r.randomness()) == expected
+    assert pr.host_syncs > 20
+    pr.set_host_transcript(False)
     # proving twice with the same inputs is deterministic; other masks change the proof
     assert pr.prove(r.witness, r.randomness()) == got
     other = pr.prove(r.witness, r.randomness(seed=3))
