@@ -244,7 +244,10 @@ def main():
     # creates the CUDA context).  Off by default: measured on a B200 box it costs ~170 us per round trip (one proof in
     # flight 12.7 -> 34 ms, 135 -> 87 proofs/s); only for hosts with far fewer cores than waiting threads.
     _, world_, local_ = env_rank()
-    blocking = os.environ.get("PK_BLOCKING_SYNC", "") == "1" and pk.lib().pk_set_blocking_sync(local_, 1) == 0
+    # Default with the device transcript (one host synchronisation per proof): blocking, the waiting threads cost no cores.
+    host_ts = os.environ.get("PK_HOST_TRANSCRIPT", "") == "1"
+    want_blocking = os.environ.get("PK_BLOCKING_SYNC", "0" if host_ts else "1") == "1"
+    blocking = want_blocking and pk.lib().pk_set_blocking_sync(local_, 1) == 0
     import torch
     from tools.dist_util import Dist, aggregate_throughput
     dd = Dist()
@@ -395,6 +398,9 @@ def main():
         value = aggregate_throughput(region, world, dev_ms)
         line["config"]["in_flight_proofs_per_gpu"] = n_fl
         line["config"]["host_wait"] = "blocking sync" if blocking else "spin (CUDA default)"
+        line["config"]["transcript"] = ("host sponge (a round trip per challenge)" if host_ts else
+                                        "device-resident sponge (host enqueues only)")
+        line["host_syncs_per_proof"] = int(prover.host_syncs)
         line["config"]["host_cores"] = os.cpu_count()
         line["config"]["timing"] = (f"value and e2e: MEDIAN of {REPEATS} timed repetitions of {region} proofs each (a multiple of "
                                     f"K = {args.steps}, at least {MIN_REGION_STEPS}: >= 1 s per repetition), {n_fl} proofs in flight handed "

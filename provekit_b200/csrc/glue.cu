@@ -227,23 +227,37 @@ int launch_expand_powers(cudaStream_t st, void* out, const void* alpha, int m0, 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) k_stir_indices(const uint32_t* bytes_words, int nq, int nb, int folded_log, uint64_t* idx,
                                                      uint32_t* n_idx) {
-    if (threadIdx.x) return;
+    __shared__ uint64_t s[OPEN_MAX_QUERIES];  // the sort runs in shared memory: global read-modify-writes cost ~1 us each
     const uint8_t* bytes = reinterpret_cast<const uint8_t*>(bytes_words);
     const uint64_t mask = folded_log >= 64 ? ~0ull : (((uint64_t)1 << folded_log) - 1);
-    int n = 0;
-    for (int i = 0; i < nq; i++) {
+    for (int i = threadIdx.x; i < nq; i += 32) {
         uint64_t v = 0;
         for (int j = 0; j < nb; j++) v = (v << 8) | bytes[i * nb + j];
-        v &= mask;
-        // insertion into the sorted, duplicate-free prefix idx[0..n)
-        int pos = n;
-        while (pos > 0 && idx[pos - 1] > v) pos--;
-        if (pos > 0 && idx[pos - 1] == v) continue;
-        for (int k = n; k > pos; k--) idx[k] = idx[k - 1];
-        idx[pos] = v;
-        n++;
+        s[i] = v & mask;
     }
-    *n_idx = (uint32_t)n;
+    __syncwarp();
+    // rank sort without duplicates: an element survives if no EARLIER element has the same value; its position is the
+    // number of surviving smaller values
+    __shared__ uint8_t first[OPEN_MAX_QUERIES];
+    for (int i = threadIdx.x; i < nq; i += 32) {
+        const uint64_t v = s[i];
+        bool f = true;
+        for (int j = 0; j < i; j++) f &= s[j] != v;
+        first[i] = f;
+    }
+    __syncwarp();
+    int mine = 0;
+    for (int i = threadIdx.x; i < nq; i += 32) {
+        if (!first[i]) continue;
+        mine++;
+        const uint64_t v = s[i];
+        int rank = 0;
+        for (int j = 0; j < nq; j++) rank += (first[j] && s[j] < v) ? 1 : 0;
+        idx[rank] = v;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, d);
+    if (threadIdx.x == 0) *n_idx = (uint32_t)mine;
 }
 int launch_stir_indices(cudaStream_t st, const uint32_t* bytes_words, int nq, int nb, int folded_log, uint64_t* idx, uint32_t* n_idx) {
     k_stir_indices<<<1, 32, 0, st>>>(bytes_words, nq, nb, folded_log, idx, n_idx);

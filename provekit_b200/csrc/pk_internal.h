@@ -14,6 +14,11 @@
 struct pk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    // Private stream-ordered memory pool.  With the device transcript the host enqueues a whole proof ahead of the GPU; on the
+    // shared default pool the allocator then recycles blocks ACROSS the streams of the proofs in flight by inserting
+    // inter-stream dependencies, which serialises them.  One pool per ctx (= per stream) keeps reuse stream-local.
+    cudaMemPool_t pool = nullptr;
+    bool shared_pool = false;
     std::string err;
     uint64_t launches = 0;
     // small fixed work areas
@@ -88,6 +93,9 @@ struct ProfScope {
     }
 };
 int set_err(pk_ctx* ctx, int code, const char* fmt, ...);
+inline cudaError_t ctx_malloc(pk_ctx* ctx, void** p, size_t bytes) {
+    return ctx->pool ? cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->stream) : cudaMallocAsync(p, bytes, ctx->stream);
+}
 int ensure_twiddles(pk_ctx* ctx, int log_m);
 int ensure_scratch(pk_ctx* ctx, size_t elems);
 int ensure_tables(pk_ctx* ctx, size_t elems);

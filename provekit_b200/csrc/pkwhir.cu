@@ -111,11 +111,21 @@ int pk_ctx_create(int device, pk_ctx** out) {
         pk_ctx_destroy(ctx);
         return PK_ERR_CUDA;
     }
-    {   // keep freed blocks cached in the stream-ordered pool: allocation becomes a pointer bump
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    {   // private pool; freed blocks stay cached in it: allocation becomes a pointer bump
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&ctx->pool, &props) != cudaSuccess) {
+            cudaGetLastError();
+            ctx->pool = nullptr;
+            cudaDeviceGetDefaultMemPool(&ctx->pool, device);  // fall back to the shared pool (never destroyed by us)
+            ctx->shared_pool = true;
+        }
+        if (ctx->pool) {
             uint64_t thr = ~0ULL;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr);
         }
     }
     *out = ctx;
@@ -137,6 +147,7 @@ void pk_ctx_destroy(pk_ctx* ctx) {
     cudaFree(ctx->d_small);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->pool && !ctx->shared_pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -157,7 +168,7 @@ int pk_buf_alloc(pk_ctx* ctx, size_t n, pk_buf** out) {
     *out = nullptr;
     pk_buf* b = new pk_buf();
     b->n = n;
-    cudaError_t e = cudaMallocAsync(&b->d, n ? n * 32 : 32, ctx->stream);
+    cudaError_t e = ctx_malloc(ctx, &b->d, n ? n * 32 : 32);
     if (e != cudaSuccess) {
         delete b;
         return set_err(ctx, PK_ERR_OOM, "cudaMalloc(%zu elems): %s", n, cudaGetErrorString(e));
@@ -461,8 +472,7 @@ int commit_batch_dev(pk_ctx* ctx, const void* const* coeffs, int batch, int log_
     c->w = ((size_t)batch) << fold;
     c->L = (size_t)1 << (log_n + log_inv_rate - fold);
     c->depth = log_n + log_inv_rate - fold;
-    if (cudaMallocAsync(&c->leaves, c->L * c->w * 32, ctx->stream) != cudaSuccess ||
-        cudaMallocAsync(&c->nodes, 2 * c->L * 32, ctx->stream) != cudaSuccess) {
+    if (ctx_malloc(ctx, &c->leaves, c->L * c->w * 32) != cudaSuccess || ctx_malloc(ctx, &c->nodes, 2 * c->L * 32) != cudaSuccess) {
         pk_commit_free(ctx, c);
         return set_err(ctx, PK_ERR_OOM, "commit_batch: out of device memory");
     }
@@ -663,7 +673,7 @@ int dev_eval_eq_roots(pk_ctx* ctx, const uint64_t* exps_dev, const uint32_t* cou
         return PK_OK;
     }
     void *sparse = nullptr, *lv = nullptr;
-    if (cudaMallocAsync(&sparse, D * 32, ctx->stream) != cudaSuccess || cudaMallocAsync(&lv, D * 32, ctx->stream) != cudaSuccess) {
+    if (ctx_malloc(ctx, &sparse, D * 32) != cudaSuccess || ctx_malloc(ctx, &lv, D * 32) != cudaSuccess) {
         if (sparse) cudaFreeAsync(sparse, ctx->stream);
         return set_err(ctx, PK_ERR_OOM, "eval_eq_roots: out of device memory");
     }
