@@ -287,6 +287,7 @@ struct NttPass {
     const fr* in;
     fr* out;           // scratch (non-last pass)
     const fr* W;       // twiddle table, order 2^tbl_log
+    const fr* Wcan;    // the same table as canonical integers, or null: when set the codeword is emitted canonical
     int tbl_shift;     // omega_M^e = W[e << tbl_shift]
     int L, l, S, logE, logM;
     int first, last;
@@ -320,11 +321,14 @@ __global__ void __launch_bounds__(256) k_ntt_pass(NttPass P) {
         fr x;
         if (P.first) {
             x = fr_load_nc(&P.in[(size_t)q * 16 + P.col0 + k]);
-            if (s) {  // coset twist omega_M^(s*q)
-                uint32_t e = s * q;
+            if (s || P.Wcan) {  // coset twist omega_M^(s*q); a canonical twiddle also strips the Montgomery factor
+                uint32_t e = (s * q) & ((halfM << 1) - 1u);
                 bool neg = e >= halfM;
                 e &= halfM - 1;
-                if (e) x = fr_mul(x, fr_load_nc(&P.W[(size_t)e << P.tbl_shift]));
+                if (e)
+                    x = fr_mul(x, fr_load_nc(&(P.Wcan ? P.Wcan : P.W)[(size_t)e << P.tbl_shift]));
+                else if (P.Wcan)
+                    x = fr_from_mont(x);
                 if (neg) x = fr_neg(x);
             }
         } else {
@@ -372,7 +376,7 @@ __global__ void __launch_bounds__(256) k_ntt_pass(NttPass P) {
 // columns [col0, col0 + 2^nc_log) of one polynomial; peers: n_peers leaf blocks of (rows / n_peers) rows each
 int launch_rs_encode_cols(cudaStream_t st, const void* coeffs, int log_n, int log_inv_rate, int fold, int col0, int nc_log,
                           void* const* peers, int n_peers, size_t leaf_stride, size_t col_offset, void* scratch,
-                          const void* table, int table_log_m) {
+                          const void* table, int table_log_m, const void* twist_canonical) {
     // fold must be 4 (16 columns): FoldingFactor::Constant(4), provekit/r1cs-compiler/src/whir_r1cs.rs:44
     int L = log_n - fold;
     int logE = log_inv_rate;
@@ -392,6 +396,7 @@ int launch_rs_encode_cols(cudaStream_t st, const void* coeffs, int log_n, int lo
         P.in = (const fr*)(P.first ? coeffs : scratch);
         P.out = (fr*)scratch;
         P.W = (const fr*)table;
+        P.Wcan = (const fr*)twist_canonical;
         P.tbl_shift = table_log_m - logM;
         P.L = L;
         P.S = S;
@@ -414,10 +419,11 @@ int launch_rs_encode_cols(cudaStream_t st, const void* coeffs, int log_n, int lo
     return launches;
 }
 int launch_rs_encode(cudaStream_t st, const void* coeffs, int log_n, int log_inv_rate, int fold, void* out,
-                     size_t leaf_stride, size_t col_offset, void* scratch, const void* table, int table_log_m) {
+                     size_t leaf_stride, size_t col_offset, void* scratch, const void* table, int table_log_m,
+                     const void* twist_canonical) {
     void* peers[1] = {out};
     return launch_rs_encode_cols(st, coeffs, log_n, log_inv_rate, fold, 0, 4, peers, 1, leaf_stride, col_offset, scratch, table,
-                                 table_log_m);
+                                 table_log_m, twist_canonical);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1169,7 +1175,7 @@ cudaError_t init_kernel_attributes() {
     if ((e = cudaFuncSetAttribute(k_wavelet_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
     if ((e = cudaFuncSetAttribute(k_wavelet_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
     if ((e = cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, smem + 32768))) return e;
-    return cudaSuccess;
+    return init_ntt_attributes();
 }
 
 }  // namespace pk

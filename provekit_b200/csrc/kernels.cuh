@@ -35,14 +35,36 @@ int launch_twiddle_table(cudaStream_t st, void* table, int log_m, const uint32_t
 
 // K1 RS encode: coeffs (2^log_n) -> out[(row)*leaf_stride + col_offset + k]; scratch: 2^(log_n+log_inv_rate)
 // table: twiddles for M = 2^(log_n + log_inv_rate - fold), table_log_m >= that (strided use)
+// twist_canonical (optional): table of CANONICAL twiddles of the same order; when given, the codeword comes out as
+// canonical integers instead of Montgomery-form elements
 int launch_rs_encode(cudaStream_t st, const void* coeffs, int log_n, int log_inv_rate, int fold, void* out,
-                     size_t leaf_stride, size_t col_offset, void* scratch, const void* table, int table_log_m);
+                     size_t leaf_stride, size_t col_offset, void* scratch, const void* table, int table_log_m,
+                     const void* twist_canonical = nullptr);
+
+// ---- ntt.cu: the TMA-staged radix-8 RS-encode (2^S points x 4 columns per tile, tile-major scratch between passes) ----
+constexpr int NTT8_MAX_S = 9;  // 2^9 points x 128 B = 64 KB tile (+ 16 KB twiddle slice): two CTAs per SM
+constexpr int NTT8_MIN_L = 7;  // shorter columns (2^L points) stay on k_ntt_pass
+struct NttR8 {
+    const fr* in;      // first pass: coefficients (point q = 16 columns, 512 B); later passes: this pass's tile-major scratch
+    fr* out;           // the next pass's tile-major scratch, or the leaves (last pass)
+    const fr* tw;      // per-pass twiddle slices [Lo][2^S] (launch_ntt_tile_twiddles)
+    const fr* Wtwist;  // coset-twist table of order 2^(logM + tbl_shift): Montgomery, or canonical when `canonical`
+    int tbl_shift;
+    int L, l, S, logE, logM;
+    int first, last, canonical;
+    int l_next, S_next;
+    size_t leaf_stride, col_offset;
+};
+int launch_ntt_tile_twiddles(cudaStream_t st, void* out, const void* W, int table_log_m, int L, int l, int S);
+int launch_ntt_r8_pass(cudaStream_t st, const NttR8& P);
+size_t ntt_r8_smem_bytes(int S);
+cudaError_t init_ntt_attributes();
 
 // sharded variant: only columns [col0, col0 + 2^nc_log) of the polynomial; row r of the codeword is stored into
 // peers[r / (rows / n_peers)] (device pointers of this or of peer GPUs) at its local row index
 int launch_rs_encode_cols(cudaStream_t st, const void* coeffs, int log_n, int log_inv_rate, int fold, int col0, int nc_log,
                           void* const* peers, int n_peers, size_t leaf_stride, size_t col_offset, void* scratch,
-                          const void* table, int table_log_m);
+                          const void* table, int table_log_m, const void* twist_canonical = nullptr);
 
 // K2 Merkle: leaves Montgomery, nodes canonical heap order
 // canonical: the leaf elements are canonical integers already (no Montgomery conversion before hashing)

@@ -27,8 +27,16 @@ struct pk_ctx {
     uint64_t* h_result = nullptr; // pinned, 64 field elements
     unsigned long long* d_best = nullptr;
     // grow-on-demand work areas
-    void* d_twiddles = nullptr;
+    void* d_twiddles = nullptr;      // omega_M^e, e < M/2, Montgomery form
+    void* d_twiddles_can = nullptr;  // the same values as canonical integers (coset twist of a canonical-output RS-encode)
     int twiddle_log_m = 0;
+    // pass plans of the TMA-staged RS-encode per column length 2^L: stage split and per-pass twiddle slices
+    struct NttPlan {
+        int L = 0, npass = 0;
+        int S[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
+        void* tw[4] = {nullptr, nullptr, nullptr, nullptr};
+    };
+    std::vector<NttPlan> ntt_plans;
     void* d_scratch = nullptr;    // NTT scratch
     size_t scratch_elems = 0;
     void* d_tables = nullptr;     // tensor tables / small uploads

@@ -51,9 +51,11 @@ int ensure_twiddles(pk_ctx* ctx, int log_m) {
     if (log_m > 28) return set_err(ctx, PK_ERR_INVALID_ARG, "domain 2^%d exceeds the field's 2-adicity", log_m);
     PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->d_twiddles) cudaFree(ctx->d_twiddles);
-    ctx->d_twiddles = nullptr;
+    if (ctx->d_twiddles_can) cudaFree(ctx->d_twiddles_can);
+    ctx->d_twiddles = ctx->d_twiddles_can = nullptr;
     ctx->twiddle_log_m = 0;
     PK_CUDA(ctx, cudaMalloc(&ctx->d_twiddles, ((size_t)32 << (log_m - 1))));
+    PK_CUDA(ctx, cudaMalloc(&ctx->d_twiddles_can, ((size_t)32 << (log_m - 1))));
     uint32_t pow2[28][8];
     pkh::Fr g = pkh::root_of_unity(log_m);
     for (int b = 0; b < 28; b++) {
@@ -61,8 +63,38 @@ int ensure_twiddles(pk_ctx* ctx, int log_m) {
         g = pkh::sqr(g);
     }
     ctx->launches += launch_twiddle_table(ctx->stream, ctx->d_twiddles, log_m, &pow2[0][0]);
+    PK_CUDA(ctx, cudaMemcpyAsync(ctx->d_twiddles_can, ctx->d_twiddles, (size_t)32 << (log_m - 1), cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->launches += launch_to_mont(ctx->stream, ctx->d_twiddles_can, (size_t)1 << (log_m - 1), false);
     PK_CUDA(ctx, cudaGetLastError());
     ctx->twiddle_log_m = log_m;
+    return PK_OK;
+}
+// stage split of a 2^L-point column NTT into passes of at most NTT8_MAX_S stage bits (balanced: 17 -> 9 + 8) and the
+// twiddle slice table of every pass (built once per L, kept for the life of the ctx)
+static int ensure_ntt_plan(pk_ctx* ctx, int L, const pk_ctx::NttPlan** out) {
+    for (const pk_ctx::NttPlan& p : ctx->ntt_plans)
+        if (p.L == L) {
+            *out = &p;
+            return PK_OK;
+        }
+    PK_TRY(ensure_twiddles(ctx, L));
+    pk_ctx::NttPlan plan;
+    plan.L = L;
+    plan.npass = (L + NTT8_MAX_S - 1) / NTT8_MAX_S;
+    if (plan.npass > 4) return set_err(ctx, PK_ERR_INVALID_ARG, "rs_encode: column length 2^%d unsupported", L);
+    int done = 0;
+    for (int p = 0; p < plan.npass; p++) {
+        const int S = (L - done + (plan.npass - p) - 1) / (plan.npass - p);
+        plan.S[p] = S;
+        plan.l[p] = L - done - S;
+        PK_CUDA(ctx, cudaMalloc(&plan.tw[p], (size_t)32 << (plan.l[p] + S)));
+        ctx->launches += launch_ntt_tile_twiddles(ctx->stream, plan.tw[p], ctx->d_twiddles, ctx->twiddle_log_m, L, plan.l[p], S);
+        done += S;
+    }
+    PK_CUDA(ctx, cudaGetLastError());
+    ctx->ntt_plans.reserve(16);  // pointers handed out stay valid
+    ctx->ntt_plans.push_back(plan);
+    *out = &ctx->ntt_plans.back();
     return PK_OK;
 }
 
@@ -142,6 +174,9 @@ void pk_ctx_destroy(pk_ctx* ctx) {
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     cudaFree(ctx->d_best);
     cudaFree(ctx->d_twiddles);
+    cudaFree(ctx->d_twiddles_can);
+    for (pk_ctx::NttPlan& p : ctx->ntt_plans)
+        for (int i = 0; i < 4; i++) cudaFree(p.tw[i]);
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_tables);
     cudaFree(ctx->d_small);
@@ -384,17 +419,50 @@ int pk_coeffs_to_evals(pk_ctx* ctx, pk_buf* buf, int log_n) {
     PK_BIND(ctx); return wavelet(ctx, buf, log_n, false); }
 
 // ---- commit ------------------------------------------------------------------------------------
+// canonical: emit the codeword as canonical integers (the Merkle leaf hash's input form) instead of Montgomery elements
 static int rs_encode_raw(pk_ctx* ctx, const void* coeffs, int log_n, int log_inv_rate, int fold, void* leaves,
-                         size_t leaf_stride, size_t col_offset) {
+                         size_t leaf_stride, size_t col_offset, bool canonical = false) {
     PK_CHECK(ctx, fold == 4, "only FoldingFactor::Constant(4) is supported (r1cs-compiler/src/whir_r1cs.rs:44)");
     PK_CHECK(ctx, log_n >= fold && log_inv_rate >= 0 && log_n + log_inv_rate <= 28, "rs_encode: bad sizes");
-    int logM = log_n - fold + log_inv_rate;
+    const int L = log_n - fold, logM = L + log_inv_rate;
     PK_TRY(ensure_twiddles(ctx, logM));
     PK_TRY(ensure_scratch(ctx, (size_t)1 << (log_n + log_inv_rate)));
-    {
+    const bool use_r8 = L >= NTT8_MIN_L && !(std::getenv("PK_NTT_LEGACY") && std::getenv("PK_NTT_LEGACY")[0] == '1');
+    if (!use_r8) {  // tiny transforms: the register-staged radix-2 kernel
         ProfScope ps(ctx, PROF_NTT);
         ctx->launches += launch_rs_encode(ctx->stream, coeffs, log_n, log_inv_rate, fold, leaves, leaf_stride, col_offset,
-                                          ctx->d_scratch, ctx->d_twiddles, ctx->twiddle_log_m);
+                                          ctx->d_scratch, ctx->d_twiddles, ctx->twiddle_log_m, canonical ? ctx->d_twiddles_can : nullptr);
+        PK_CUDA(ctx, cudaGetLastError());
+        return PK_OK;
+    }
+    const pk_ctx::NttPlan* plan;
+    PK_TRY(ensure_ntt_plan(ctx, L, &plan));
+    // two scratch halves ping-pong between passes (a pass may not overwrite the layout it is still reading)
+    const size_t cw = (size_t)1 << (log_n + log_inv_rate);
+    if (plan->npass > 2) PK_TRY(ensure_scratch(ctx, 2 * cw));
+    ProfScope ps(ctx, PROF_NTT);
+    for (int p = 0; p < plan->npass; p++) {
+        NttR8 P = {};
+        P.first = p == 0;
+        P.last = p == plan->npass - 1;
+        char* ping = (char*)ctx->d_scratch + (size_t)(p & 1) * cw * 32;
+        char* pong = (char*)ctx->d_scratch + (size_t)((p + 1) & 1) * cw * 32;
+        P.in = (const fr*)(P.first ? coeffs : (const void*)pong);
+        P.out = (fr*)(P.last ? leaves : (void*)ping);
+        P.tw = (const fr*)plan->tw[p];
+        P.Wtwist = (const fr*)(canonical ? ctx->d_twiddles_can : ctx->d_twiddles);
+        P.tbl_shift = ctx->twiddle_log_m - (logM < 1 ? 1 : logM);
+        P.L = L;
+        P.l = plan->l[p];
+        P.S = plan->S[p];
+        P.logE = log_inv_rate;
+        P.logM = logM < 1 ? 1 : logM;
+        P.canonical = canonical ? 1 : 0;
+        P.l_next = P.last ? 0 : plan->l[p + 1];
+        P.S_next = P.last ? 0 : plan->S[p + 1];
+        P.leaf_stride = leaf_stride;
+        P.col_offset = col_offset;
+        ctx->launches += launch_ntt_r8_pass(ctx->stream, P);
     }
     PK_CUDA(ctx, cudaGetLastError());
     return PK_OK;
@@ -476,8 +544,10 @@ int commit_batch_dev(pk_ctx* ctx, const void* const* coeffs, int batch, int log_
         pk_commit_free(ctx, c);
         return set_err(ctx, PK_ERR_OOM, "commit_batch: out of device memory");
     }
+    // the commitment keeps its codeword as canonical integers: the leaf hash consumes that form directly
+    c->canonical_leaves = !(std::getenv("PK_LEAVES_MONTGOMERY") && std::getenv("PK_LEAVES_MONTGOMERY")[0] == '1');
     for (int b = 0; b < batch; b++) {
-        int rc = rs_encode_raw(ctx, coeffs[b], log_n, log_inv_rate, fold, c->leaves, c->w, (size_t)b << fold);
+        int rc = rs_encode_raw(ctx, coeffs[b], log_n, log_inv_rate, fold, c->leaves, c->w, (size_t)b << fold, c->canonical_leaves);
         if (rc != PK_OK) {
             pk_commit_free(ctx, c);
             return rc;
@@ -556,6 +626,7 @@ int pk_commit_open(pk_ctx* ctx, const pk_commitment* c, const uint64_t* sorted_i
     char* d_rows = (char*)ctx->d_tables;
     char* d_path = d_rows + n_rows * 32;
     ctx->launches += launch_gather_rows(ctx->stream, c->leaves, c->w, (const uint64_t*)ctx->d_small, n_idx, d_rows);
+    if (c->canonical_leaves) ctx->launches += launch_to_mont(ctx->stream, d_rows, n_rows, true);  // the ABI returns field elements
     ctx->launches += launch_gather_paths(ctx->stream, c->nodes, c->L, (const uint64_t*)ctx->d_small, n_idx, depth, d_path);
     PK_CUDA(ctx, cudaGetLastError());
     PK_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage, d_rows, (n_rows + n_path) * 32, cudaMemcpyDeviceToHost, ctx->stream));

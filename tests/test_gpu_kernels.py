@@ -89,7 +89,10 @@ def test_wavelet_vs_oracle(ctx, orc, log_n):
     buf.free()
 
 
-@pytest.mark.parametrize("log_n,rate", [(4, 1), (4, 4), (5, 13), (9, 10), (11, 1), (12, 2), (13, 7), (17, 4), (18, 1), (20, 1)])
+# column length 2^L, L = log_n - 4: L < 7 runs the register-staged radix-2 kernel, L >= 7 the TMA-staged radix-8 kernel with one
+# pass (L <= 9: 11, 12, 13), two (17 -> 7+6, 18 -> 7+7, 20 -> 8+8, 21 -> 9+8, 22 -> 9+9) or three (23 -> 7+6+6)
+@pytest.mark.parametrize("log_n,rate", [(4, 1), (4, 4), (5, 13), (9, 10), (10, 3), (11, 1), (11, 0), (12, 2), (13, 7), (14, 1), (17, 4),
+                                        (18, 1), (20, 1), (21, 1), (22, 1), (23, 1)])
 def test_rs_encode_vs_oracle(ctx, orc, log_n, rate):
     a = rng_fr(1000 + log_n, 1 << log_n)
     rows = 1 << (log_n + rate - 4)
