@@ -38,7 +38,7 @@ from tools import workload as wl  # noqa: E402
 
 REPEATS = 5          # timed repetitions; the MEDIAN is reported (config.timing)
 MIN_REGION_STEPS = 150   # a timed repetition covers ceil(MIN_REGION_STEPS / K) * K proofs (>= 1 s), whatever --steps is
-IN_FLIGHT = 8        # independent proofs in flight per GPU, fixed (not derived from --steps)
+IN_FLIGHT = 12       # independent proofs in flight per GPU, fixed (not derived from --steps)
 
 WORKLOADS = {
     # configs[1]: poseidon-rounds shapes (fixture poseidon-1000.nps): m = 21, m_0 = 20
@@ -229,6 +229,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="poseidon-1000", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded commitment / sumcheck measurements")
+    ap.add_argument("--sharded-log-n", type=int, default=23,
+                    help="N > 1: coefficients per polynomial of the sharded commitment (BASELINE configs[3]: 2 x 2^23)")
     ap.add_argument("--in-flight", type=int, default=0,
                     help=f"independent proofs in flight per GPU (own ctx/stream/host thread each), 0 = {IN_FLIGHT}")
     args = ap.parse_args()
@@ -392,6 +395,20 @@ def main():
     hm_ms = max_over_ranks(max(hm_ms, hm_wall))
     clocks = sampler.finish() if sampler else None
 
+    # ---- N > 1: the SHARDED path of SURVEY 8e next to the replicas (column-sharded NTT -> peer-store exchange -> row-sharded
+    # Merkle -> all-gather of sub-roots; sharded sumchecks), each checked against the single-GPU result on rank 0 ----
+    sharded_info = None
+    if world > 1 and not args.no_sharded:
+        from provekit_b200 import sharded
+        try:
+            sharded_info = sharded.bench_sharded(pk, ctx, dist, rank, world, torch.device("cuda", local_rank),
+                                                 log_n_commit=args.sharded_log_n, log_n_sumcheck=args.sharded_log_n - 1,
+                                                 barrier=barrier, max_over_ranks=max_over_ranks)
+        except Exception as e:  # the replica numbers stand on their own: report the failure instead of losing the line
+            sharded_info = {"error": f"{type(e).__name__}: {e}"}
+            if rank != 0:
+                sharded_info = None
+
     if rank == 0:
         peak, peak_src = measured_peak()
         line = base_line(args, args.workload, r1cs)
@@ -445,6 +462,8 @@ def main():
                                     "achieved": nb / (ntt_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                                     "frac": nb / (ntt_ms / 1e3) / 1e9 / peak, "traffic": ntt_traffic, "algorithmic_bytes": nb,
                                     "ms_per_proof": ntt_ms}
+        if sharded_info is not None:
+            line["sharded"] = sharded_info
         line["host_stage_s_last_proof"] = dict(zip(["commit", "h2d", "zk_sumcheck", "whir_sumcheck", "pow", "open", "spmv_weights",
                                                     "other", "total"], [round(x, 5) for x in stage_t]))
         if world == 1 and not args.no_cpu_baseline:

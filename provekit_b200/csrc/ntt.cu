@@ -153,11 +153,13 @@ __global__ void __launch_bounds__(256, 2) k_ntt_r8(NttR8 P) {
     uint4* tile = reinterpret_cast<uint4*>(smem_bytes);
     fr* tw = reinterpret_cast<fr*>(smem_bytes + (size_t)npts * NTT8_RUN_BYTES);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_bytes + (size_t)npts * NTT8_RUN_BYTES + (size_t)npts * 32);
-    // consecutive blocks = the 4 column groups of the same rows: their 128-byte runs are neighbours in HBM
+    // consecutive blocks = the 4 column groups x all cosets of the same rows: the 128-byte runs of the column groups are
+    // neighbours in HBM, and every coset re-reads the same coefficients, so the first reader pulls them from HBM and the
+    // others (scheduled right next to it) hit L2
     const uint32_t cg = blockIdx.x & (16 / NTT8_NC - 1);
     const uint32_t tile_lin = blockIdx.x / (16 / NTT8_NC);
-    const uint32_t s = tile_lin >> (L - S);
-    const uint32_t t = tile_lin & ((1u << (L - S)) - 1u);
+    const uint32_t s = tile_lin & ((1u << P.logE) - 1u);
+    const uint32_t t = tile_lin >> P.logE;
     const uint32_t Lo = t & ((1u << l) - 1u), H = t >> l;
     const uint32_t qbase = (H << (l + S)) | Lo;
     const uint32_t tile_bytes = (uint32_t)npts * NTT8_RUN_BYTES, tw_bytes = (uint32_t)npts * 32;

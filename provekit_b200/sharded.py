@@ -197,3 +197,215 @@ def sharded_whir_sumcheck(backend, gather: Gather, local_p, local_w, log_n: int,
     for b in src + dst:
         backend.free(b)
     return msgs
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Sharded commitment (BASELINE configs[3]): the codeword's COLUMNS are sharded across ranks for the NTT (no
+# communication inside it), its ROWS (Merkle leaves) for hashing.  The exchange between the two layouts is fused into the
+# last NTT pass as peer stores into CUDA-IPC mapped leaf blocks (pk_rs_encode_sharded); the G sub-tree roots are
+# all-gathered (32 B per rank) and the top log2 G levels hashed by every rank (pk_merkle_combine_roots).
+# ------------------------------------------------------------------------------------------------------------------
+def to_montgomery(canon) -> np.ndarray:
+    return _to_limbs(_to_int(canon) * (1 << 256) % P)
+
+
+class ShardedCommit:
+    def __init__(self, ctx, dist, rank: int, world: int, polys, log_n: int, rate: int = 1, coll_device=None):
+        """polys: this rank's device buffers of the `batch` coefficient vectors (every rank holds all of them: the host
+        uploads the witness to every GPU); dist: torch.distributed (None when world == 1); coll_device: device of the
+        collective tensors (a cuda device under NCCL, None = host tensors for gloo)."""
+        self.ctx, self.dist, self.rank, self.world, self.polys = ctx, dist, rank, world, polys
+        self.log_n, self.rate, self.batch = log_n, rate, len(polys)
+        self.rows = 1 << (log_n + rate - 4)
+        self.w = 16 * self.batch
+        if world not in (1, 2, 4, 8) or self.rows < world or (16 * self.batch) % world:
+            raise ValueError("world must be 1, 2, 4 or 8 and divide the column count")
+        self.per = self.rows // world
+        cols_per_rank = 16 * self.batch // world
+        self.groups = {}
+        for c in range(rank * cols_per_rank, (rank + 1) * cols_per_rank):
+            self.groups.setdefault(c // 16, []).append(c % 16)
+        self.leaves = ctx.buffer_shared(self.per * self.w)
+        self.nodes = ctx.buffer(2 * self.per)
+        self.coll_device = coll_device
+        self.opened = []
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, ctx.ipc_export(self.leaves))
+            self.peers = []
+            for r in range(world):
+                if r == rank:
+                    self.peers.append(self.leaves.device_ptr)
+                else:
+                    p = ctx.ipc_open(handles[r])
+                    self.opened.append(p)
+                    self.peers.append(p)
+        else:
+            self.peers = [self.leaves.device_ptr]
+
+    def commit(self) -> np.ndarray:
+        """-> canonical root (4 limbs), identical on every rank and to the single-GPU pk_commit_batch root"""
+        ctx = self.ctx
+        for b, cs in self.groups.items():
+            ctx.rs_encode_sharded(self.polys[b], self.log_n, self.rate, min(cs), len(cs), self.peers, self.w, 16 * b)
+        ctx.sync()
+        if self.world > 1:
+            self.dist.barrier()  # a rank's rows are complete only after ALL peers finished storing into them
+        ctx.merkle_build(self.leaves, self.per, self.w, self.nodes)
+        sub = self.nodes.download(1, 1)  # canonical sub-tree root
+        if self.world == 1:
+            return ctx.merkle_combine_roots(sub)
+        import torch
+        mine = torch.from_numpy(sub.view(np.int64).reshape(-1).copy())
+        if self.coll_device is not None:
+            mine = mine.to(self.coll_device)
+        out = torch.empty(self.world * 4, dtype=torch.int64, device=mine.device)
+        self.dist.all_gather_into_tensor(out, mine)
+        return ctx.merkle_combine_roots(out.cpu().numpy().view(np.uint64).reshape(self.world, 4))
+
+    def close(self):
+        for p in self.opened:
+            self.ctx.ipc_close(p)
+        self.opened = []
+        self.leaves.free()
+        self.nodes.free()
+
+
+def bench_sharded(pk, ctx, dist, rank: int, world: int, coll_device, log_n_commit: int = 23, log_n_sumcheck: int = 22,
+                  steps: int = 3, warmup: int = 1, seed: int = 4, barrier=None, max_over_ranks=None, gather_group=None):
+    """The sharded path of SURVEY 8e on `world` ranks (one process per GPU): commitment of 2 x 2^log_n_commit coefficients
+    (BASELINE configs[3]) and both sumchecks, each checked against the single-GPU run on rank 0.  Returns the dict bench.py
+    prints under "sharded" (rank 0; None elsewhere).  Device time is taken with the host clock around synchronised
+    regions (every step ends with a stream sync) and reduced with MAX over ranks."""
+    import hashlib
+    import time
+
+    def rand_fr(rng, n):  # n field elements below 2^252 < p (valid Montgomery-form arrays)
+        a = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+        a[:, 3] &= np.uint64(0x0FFFFFFFFFFFFFFF)
+        return a
+
+    barrier = barrier or (lambda: dist.barrier() if dist is not None else None)
+    max_over_ranks = max_over_ranks or (lambda x: x)
+    rng = np.random.default_rng(seed)
+    polys_host = [rand_fr(rng, 1 << log_n_commit) for _ in range(2)]
+    polys = [ctx.upload(p) for p in polys_host]
+    sc = ShardedCommit(ctx, dist, rank, world, polys, log_n_commit, 1, coll_device)
+    for _ in range(warmup):
+        root = sc.commit()
+    ctx.sync()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        root = sc.commit()
+    ctx.sync()
+    commit_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+    sc.close()
+    barrier()
+    one_ms, root_ok = None, None
+    if rank == 0:  # the single-GPU commitment of the same polynomials: reference root and reference time
+        cm = ctx.commit_batch(polys, log_n_commit, 1)
+        root_ok = bool(np.array_equal(to_montgomery(root), cm.root))
+        cm.free()
+        ctx.sync()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ctx.commit_batch(polys, log_n_commit, 1).free()
+        ctx.sync()
+        one_ms = (time.perf_counter() - t0) * 1e3 / steps
+    for p in polys:
+        p.free()
+    del polys_host
+    barrier()
+
+    # ---- sumchecks: fused exchange over CUDA-IPC peer mailboxes ----
+    def challenge(rnd, sums):
+        d = hashlib.sha256(bytes([rnd & 0xFF]) + np.ascontiguousarray(sums).tobytes()).digest()
+        return _to_limbs(int.from_bytes(d, "little") % P).reshape(1, 4)
+
+    gather = Gather(dist if world > 1 else None, None if gather_group is not None else coll_device, group=gather_group)
+    fused = world > 1
+    be = GpuBackend(ctx, fused=fused)
+    opened = []
+    if fused:
+        mbox = ctx.shard_mailbox()
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.ipc_export(mbox))
+        peers = []
+        for r in range(world):
+            if r == rank:
+                peers.append(mbox.device_ptr)
+            else:
+                opened.append(ctx.ipc_open(handles[r]))
+                peers.append(opened[-1])
+        ctx.shard_group(rank, world, peers)
+        barrier()
+    m0, m = log_n_sumcheck, log_n_sumcheck + 1
+    rng = np.random.default_rng(seed + 4)
+    zk_full = [rand_fr(rng, 1 << m0) for _ in range(4)]
+    wh_full = [rand_fr(rng, 1 << m) for _ in range(2)]
+    zk_loc = [ctx.upload(shard_low_bits(a, rank, world)) for a in zk_full]
+    wh_loc = [ctx.upload(shard_high_bits(a, rank, world)) for a in wh_full]
+
+    def step():
+        zk_in, wh_in = [b.clone() for b in zk_loc], [b.clone() for b in wh_loc]
+        ctx.sync()
+        barrier()
+        t0 = time.perf_counter()
+        zk = sharded_zk_sumcheck(be, gather, zk_in, m0, challenge)
+        ctx.sync()
+        t1 = time.perf_counter()
+        wh = sharded_whir_sumcheck(be, gather, wh_in[0], wh_in[1], m, challenge, rounds=4)
+        ctx.sync()
+        return zk, wh, (t1 - t0) * 1e3, (time.perf_counter() - t1) * 1e3
+
+    for _ in range(warmup):
+        step()
+    zk_t, wh_t = [], []
+    for _ in range(steps):
+        zk, wh, a, b = step()
+        zk_t.append(a)
+        wh_t.append(b)
+    zk_ms, wh_ms = max_over_ranks(min(zk_t)), max_over_ranks(min(wh_t))
+    msgs_ok, zk1_ms, wh1_ms = None, None, None
+    barrier()
+    if rank == 0:
+        one = Gather(None)
+        be1 = GpuBackend(ctx)
+        bufs = [ctx.upload(a) for a in zk_full]
+        ctx.sync()
+        t0 = time.perf_counter()
+        zk1 = sharded_zk_sumcheck(be1, one, bufs, m0, challenge)
+        ctx.sync()
+        zk1_ms = (time.perf_counter() - t0) * 1e3
+        bufs = [ctx.upload(a) for a in wh_full]
+        ctx.sync()
+        t0 = time.perf_counter()
+        wh1 = sharded_whir_sumcheck(be1, one, bufs[0], bufs[1], m, challenge, rounds=4)
+        ctx.sync()
+        wh1_ms = (time.perf_counter() - t0) * 1e3
+        msgs_ok = bool(len(zk) == m0 and len(wh) == 4 and all(np.array_equal(x, y) for x, y in zip(zk, zk1))
+                       and all(np.array_equal(x, y) for x, y in zip(wh, wh1)))
+    for b in zk_loc + wh_loc:
+        b.free()
+    barrier()
+    for p in opened:
+        ctx.ipc_close(p)
+    if fused:
+        ctx.L.pk_shard_group_clear(ctx.h)
+        mbox.free()
+    if rank != 0:
+        return None
+    rows = 1 << (log_n_commit + 1 - 4)
+    alg = 2 * 96 * (1 << log_n_commit) + 32 * (rows * 32 + 2 * rows - 1)
+    return {"workload": f"commit of 2 x 2^{log_n_commit} coefficients (rate 1/2, {rows} leaves x 32; BASELINE configs[3]); zk-sumcheck over "
+                        f"4 x 2^{m0}, WHIR sumcheck over 2 x 2^{m} (4 rounds)",
+            "commit_ms": commit_ms, "commit_ms_1gpu": one_ms, "speedup_vs_1": (one_ms / commit_ms) if one_ms else None,
+            "root_matches_single_gpu": root_ok, "commit_alg_gbs": alg / commit_ms / 1e6,
+            "zk_sumcheck_ms": zk_ms, "zk_sumcheck_ms_1gpu": zk1_ms, "whir_sumcheck_ms": wh_ms, "whir_sumcheck_ms_1gpu": wh1_ms,
+            "sumcheck_messages_match_single_gpu": msgs_ok,
+            "exchange": "ipc-peer-store",
+            "exchange_detail": "codeword transpose fused into the last NTT pass as NVLink peer stores into CUDA-IPC mapped leaf blocks; "
+                               "sub-tree roots all-gathered (32 B per rank); sumcheck round messages exchanged by a one-warp kernel over "
+                               "peer mailboxes and summed on the device",
+            "timing": f"host clock around stream-synchronised regions, best of {steps} steps for the sumchecks, mean for the commit, max over ranks"}

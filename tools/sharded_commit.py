@@ -18,6 +18,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import provekit_b200 as pk  # noqa: E402
+from provekit_b200 import sharded  # noqa: E402
 from tools.workload import rand_fr  # noqa: E402
 
 
@@ -26,55 +27,32 @@ def main():
     ap.add_argument("--log-n", type=int, default=23, help="coefficients per polynomial (2 polynomials, rate 1/2)")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--backend", default="nccl", choices=["nccl", "gloo"])
+    ap.add_argument("--same-device", action="store_true",
+                    help="all ranks on cuda:0 with gloo collectives: real CUDA IPC between processes on a single-GPU box")
     ap.add_argument("--check", action="store_true", help="compare the root with a single-GPU pk_commit_batch on rank 0")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
+    dev = 0 if args.same_device else local
+    backend = "gloo" if args.same_device else args.backend
+    torch.cuda.set_device(dev)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ctx = pk.Context(local)
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+        else:
+            dist.init_process_group("gloo")
+    coll_device = torch.device("cuda", dev) if backend == "nccl" else None
+    ctx = pk.Context(dev)
     stream = torch.cuda.ExternalStream(ctx.stream)
     log_n, rate, batch = args.log_n, 1, 2
     n = 1 << log_n
     rows = 1 << (log_n + rate - 4)
     w = 16 * batch
-    per = rows // world
-    assert world in (1, 2, 4, 8) and rows >= world
     # every rank holds both coefficient vectors (the host uploads the witness to all GPUs); seed shared
     rng = np.random.default_rng(4)
     polys = [ctx.upload(rand_fr(rng, n)) for _ in range(batch)]
-    # column assignment: 32 columns over `world` ranks
-    cols_per_rank = 32 // world
-    my_cols = [(c // 16, c % 16) for c in range(rank * cols_per_rank, (rank + 1) * cols_per_rank)]
-    groups = {}
-    for b, c in my_cols:
-        groups.setdefault(b, []).append(c)
-    leaves = ctx.buffer_shared(per * w)
-    nodes = ctx.buffer(2 * per)
-    handle = ctx.ipc_export(leaves)
-    if world > 1:
-        handles = [None] * world
-        dist.all_gather_object(handles, handle)
-        peers = [leaves.device_ptr if r == rank else ctx.ipc_open(handles[r]) for r in range(world)]
-    else:
-        peers = [leaves.device_ptr]
-    roots_t = torch.zeros(world, 4, dtype=torch.int64, device="cuda")
-
-    def commit():
-        for b, cs in groups.items():
-            ctx.rs_encode_sharded(polys[b], log_n, rate, min(cs), len(cs), peers, w, 16 * b)
-        ctx.sync()
-        if world > 1:
-            dist.barrier()  # every rank's rows are complete only after all peers finished storing
-        ctx.merkle_build(leaves, per, w, nodes)
-        sub = nodes.download(1, 1)  # canonical sub-tree root
-        if world > 1:
-            mine = torch.from_numpy(sub.view(np.int64).copy()).cuda()
-            dist.all_gather_into_tensor(roots_t, mine)
-            allr = roots_t.cpu().numpy().view(np.uint64)
-        else:
-            allr = sub
-        return ctx.merkle_combine_roots(allr)
+    sc = sharded.ShardedCommit(ctx, dist if world > 1 else None, rank, world, polys, log_n, rate, coll_device)
+    commit = sc.commit
 
     for _ in range(args.warmup):
         root = commit()
@@ -90,37 +68,28 @@ def main():
     ctx.sync()
     ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms], dtype=torch.float64, device=coll_device if coll_device is not None else "cpu")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ok = None
     if args.check and rank == 0:
         cm = ctx.commit_batch(polys, log_n, rate)
-        import provekit_b200  # noqa: F401
-        # cm.root is Montgomery; convert our canonical root for comparison through the library
-        ref_nodes_root = cm.root
-        ok = bool(np.array_equal(to_mont_host(root), ref_nodes_root))
+        ok = bool(np.array_equal(sharded.to_montgomery(root), cm.root))  # cm.root is Montgomery, ours canonical
         cm.free()
     if rank == 0:
         nbytes_ntt = batch * 96 * n
         nbytes_mrk = 32 * (rows * w + 2 * rows - 1)
         print(json.dumps({"workload": f"sharded commit: {batch} polynomials of 2^{log_n} coefficients, rate 1/2, {rows} leaves x {w}",
-                          "n_gpus": world, "ms_per_commit": ms, "commits_per_s": 1e3 / ms,
+                          "n_gpus": world, "same_device": args.same_device, "ms_per_commit": ms, "commits_per_s": 1e3 / ms,
                           "alg_gbs_ntt_plus_merkle": (nbytes_ntt + nbytes_mrk) / ms / 1e6,
-                          "exchange": "fused into the last NTT pass (NVLink peer stores via CUDA IPC) + NCCL all_gather of sub-roots",
+                          "exchange": "fused into the last NTT pass (peer stores via CUDA IPC) + all_gather of sub-roots over " + backend,
                           "root_matches_single_gpu": ok, "root": [int(x) for x in root]}))
     if world > 1:
-        for r, p in enumerate(peers):
-            if r != rank:
-                ctx.ipc_close(p)
+        dist.barrier()
+    sc.close()
+    ctx.close()
+    if world > 1:
         dist.destroy_process_group()
-
-
-def to_mont_host(canon):
-    P = 21888242871839275222246405745257275088548364400416034343698204186575808495617
-    v = sum(int(x) << (64 * i) for i, x in enumerate(canon))
-    m = v * (1 << 256) % P
-    return np.array([(m >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
 
 
 if __name__ == "__main__":
