@@ -247,9 +247,10 @@ def main():
     # creates the CUDA context).  Off by default: measured on a B200 box it costs ~170 us per round trip (one proof in
     # flight 12.7 -> 34 ms, 135 -> 87 proofs/s); only for hosts with far fewer cores than waiting threads.
     _, world_, local_ = env_rank()
-    # Default with the device transcript (one host synchronisation per proof): blocking, the waiting threads cost no cores.
+    # With the device transcript one host thread per GPU drives every proof in flight (enqueue / collect): nothing to
+    # oversubscribe, the CUDA default (spin) stays.
     host_ts = os.environ.get("PK_HOST_TRANSCRIPT", "") == "1"
-    want_blocking = os.environ.get("PK_BLOCKING_SYNC", "0" if host_ts else "1") == "1"
+    want_blocking = os.environ.get("PK_BLOCKING_SYNC", "0") == "1"
     blocking = want_blocking and pk.lib().pk_set_blocking_sync(local_, 1) == 0
     import torch
     from tools.dist_util import Dist, aggregate_throughput
@@ -297,6 +298,34 @@ def main():
         for p_ in provers:
             proof = p_.prove_seeded(witness, seed)
     d2h = len(proof) + 32 * (3 * (m0 + 4 * 12) + 64)  # transcript + per-round result scalars (approx.)
+
+    def run_pipeline(enq, steps):
+        """device transcript: ONE host thread keeps n_fl proofs in flight (enqueue is asynchronous, collect waits for the
+        oldest); device time from an event on stream 0 before the first launch to an event after every stream has drained"""
+        import collections
+        for c in ctxs:
+            c.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        t0 = time.perf_counter()
+        inflight, last = collections.deque(), None
+        for k in range(steps):
+            p_ = provers[k % n_fl]
+            if len(inflight) == n_fl:
+                last = inflight.popleft().collect()
+            enq(p_)
+            inflight.append(p_)
+        while inflight:
+            last = inflight.popleft().collect()
+        for i in range(1, n_fl):
+            ev = torch.cuda.Event()
+            ev.record(streams[i])
+            stream.wait_event(ev)
+        e1.record(stream)
+        for c in ctxs:
+            c.sync()
+        wall = (time.perf_counter() - t0) * 1e3
+        return max(e0.elapsed_time(e1), 0.0), wall, last
 
     def run_concurrent(fn, steps):
         """`steps` proofs handed out dynamically to the in-flight workers; device time from an event on stream 0 before the
@@ -362,23 +391,32 @@ def main():
     barrier()
     # untimed: thread start-up, first concurrent launches, and the stream-ordered memory pool growing to the footprint
     # of n_fl overlapping proofs (a pool that still grows inside the timed region costs device-wide syncs)
-    run_concurrent(lambda p_: p_.prove_staged(), 3 * n_fl)
+    # host transcript: a host thread per proof in flight (each blocks on its challenges); device transcript: one thread
+    if host_ts:
+        run_staged = lambda n: run_concurrent(lambda p_: p_.prove_staged(), n)
+        run_seeded = lambda n: run_concurrent(lambda p_: p_.prove_seeded(witness, seed), n)
+        run_masks = lambda n: run_concurrent(lambda p_: p_.prove(witness, rnd_p), n)
+    else:
+        run_staged = lambda n: run_pipeline(lambda p_: p_.enqueue_staged(), n)
+        run_seeded = lambda n: run_pipeline(lambda p_: p_.enqueue_seeded(witness, seed), n)
+        run_masks = lambda n: run_pipeline(lambda p_: p_.enqueue(witness, rnd_p), n)
+    run_staged(3 * n_fl)
     barrier()
     reps = []
     for _ in range(REPEATS):
         barrier()  # every repetition is bracketed by barriers and counted as its slowest rank
-        reps.append(max_over_ranks(run_concurrent(lambda p_: p_.prove_staged(), region)[0]))
+        reps.append(max_over_ranks(run_staged(region)[0]))
     dev_ms, dev_reps = median(reps), [round(x, 3) for x in reps]
     barrier()
     single_ms = max_over_ranks(single_ms)
 
     # ---- e2e arm: host buffers in, transcript out, every step ----
-    run_concurrent(lambda p_: p_.prove_seeded(witness, seed), n_fl)
+    run_seeded(n_fl)
     barrier()
     reps = []
     for _ in range(REPEATS):
         barrier()
-        ms2, wall2, proof = run_concurrent(lambda p_: p_.prove_seeded(witness, seed), region)
+        ms2, wall2, proof = run_seeded(region)
         reps.append((max_over_ranks(max(ms2, wall2)), ms2, wall2))
     barrier()
     e2e_ms = median([r[0] for r in reps])
@@ -387,10 +425,10 @@ def main():
                   "host_stage_s_last_proof": dict(zip(
         ["commit", "h2d", "zk_sumcheck", "whir_sumcheck", "pow", "open", "spmv_weights", "other", "total"], [round(x, 5) for x in prover.timings()]))}
     # the same with the masks as host arrays (the reference's API semantics: the host owns the randomness), one repetition
-    run_concurrent(lambda p_: p_.prove(witness, rnd_p), n_fl)
+    run_masks(n_fl)
     barrier()
     hm_steps = max(args.steps, 4 * n_fl)
-    hm_ms, hm_wall, _ = run_concurrent(lambda p_: p_.prove(witness, rnd_p), hm_steps)
+    hm_ms, hm_wall, _ = run_masks(hm_steps)
     barrier()
     hm_ms = max_over_ranks(max(hm_ms, hm_wall))
     clocks = sampler.finish() if sampler else None
@@ -415,8 +453,9 @@ def main():
         value = aggregate_throughput(region, world, dev_ms)
         line["config"]["in_flight_proofs_per_gpu"] = n_fl
         line["config"]["host_wait"] = "blocking sync" if blocking else "spin (CUDA default)"
-        line["config"]["transcript"] = ("host sponge (a round trip per challenge)" if host_ts else
-                                        "device-resident sponge (host enqueues only)")
+        line["config"]["transcript"] = ("host sponge (a round trip per challenge, one host thread per proof in flight)" if host_ts else
+                                        "device-resident sponge: one host thread per GPU enqueues the proofs in flight "
+                                        "(pk_prove_*_enqueue) and collects the proof strings (pk_prove_collect)")
         line["host_syncs_per_proof"] = int(prover.host_syncs)
         line["config"]["host_cores"] = os.cpu_count()
         line["config"]["timing"] = (f"value and e2e: MEDIAN of {REPEATS} timed repetitions of {region} proofs each (a multiple of "

@@ -247,6 +247,14 @@ int pk_prove(pk_prover *p, const uint64_t *witness, const pk_rand *rnd, uint8_t 
  * H2D staging of witness + masks, then the proof itself from the staged inputs (repeatable). */
 int pk_prover_upload_inputs(pk_prover *p, const uint64_t *witness, const pk_rand *rnd);
 int pk_prove_staged(pk_prover *p, uint8_t **out, size_t *out_len);
+/* Asynchronous form (device transcript only): *_enqueue returns as soon as the whole proof — input upload, every kernel,
+ * the proof string's D2H — is enqueued on the prover's stream; pk_prove_collect waits for it and hands out the proof
+ * string.  One host thread can keep many provers (one ctx / stream each) busy this way; the witness / mask arrays must
+ * stay valid and unchanged until collect returns.  One proof per prover at a time. */
+int pk_prove_enqueue(pk_prover *p, const uint64_t *witness, const pk_rand *rnd);
+int pk_prove_seeded_enqueue(pk_prover *p, const uint64_t *witness, const uint8_t seed[32]);
+int pk_prove_staged_enqueue(pk_prover *p);
+int pk_prove_collect(pk_prover *p, uint8_t **out, size_t *out_len);
 /* Masks drawn on the device: the reference draws them inside prove from thread_rng (a ChaCha12 stream; Fp::rand
  * rejection-samples 254-bit strings; provekit/common/src/utils/zk_utils.rs:13-22, provekit/prover/src/whir_r1cs.rs:211-225).
  * pk_rng_fill writes n uniform field elements: element i = first candidate < p among the 256-bit halves (top word

@@ -110,6 +110,10 @@ def lib() -> ctypes.CDLL:
         "pk_prover_host_syncs": (c_uint64, [vp]),
         "pk_prover_shapes": (None, [vp, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
         "pk_prove": (c_int, [vp, u64p, POINTER(Rand), POINTER(vp), POINTER(sz)]),
+        "pk_prove_enqueue": (c_int, [vp, u64p, POINTER(Rand)]),
+        "pk_prove_seeded_enqueue": (c_int, [vp, u64p, c_char_p]),
+        "pk_prove_staged_enqueue": (c_int, [vp]),
+        "pk_prove_collect": (c_int, [vp, POINTER(vp), POINTER(sz)]),
         "pk_prove_with_transcript": (c_int, [vp, u64p, POINTER(Rand), vp, vp]),
         "pk_prove_staged_with_transcript": (c_int, [vp, vp, vp]),
         "pk_free": (None, [vp]),

@@ -473,6 +473,25 @@ class Prover:
         self.ctx._chk(self.ctx.L.pk_prove_staged(self.h, byref(out), byref(n)))
         return self._take(out, n)
 
+    # ---- asynchronous form (device transcript): enqueue returns at once, collect waits for the proof string ----
+    def enqueue_staged(self):
+        self.ctx._chk(self.ctx.L.pk_prove_staged_enqueue(self.h))
+
+    def enqueue_seeded(self, witness, seed: bytes):
+        assert len(seed) == 32
+        self._w_keep = self._witness(witness)  # must stay alive until collect()
+        self.ctx._chk(self.ctx.L.pk_prove_seeded_enqueue(self.h, _p(self._w_keep), seed))
+
+    def enqueue(self, witness, rand: dict):
+        self._w_keep = self._witness(witness)
+        rs, self._r_keep = self._rand(rand)
+        self.ctx._chk(self.ctx.L.pk_prove_enqueue(self.h, _p(self._w_keep), byref(rs)))
+
+    def collect(self) -> bytes:
+        out, n = c_void_p(), c_size_t()
+        self.ctx._chk(self.ctx.L.pk_prove_collect(self.h, byref(out), byref(n)))
+        return self._take(out, n)
+
     def set_host_transcript(self, on: bool):
         """in-tree sponge on the host (True) instead of on the device (default)"""
         self.ctx._chk(self.ctx.L.pk_prover_set_host_transcript(self.h, 1 if on else 0))

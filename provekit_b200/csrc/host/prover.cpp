@@ -175,6 +175,9 @@ struct pk_prover {
     pk_buf *masked_w = nullptr, *g_w = nullptr, *masked_h = nullptr, *g_h = nullptr;
     bool staged = false;
     FlowMem mem;
+    bool pending = false;       // a proof was enqueued (pk_prove_*_enqueue) and not collected yet
+    size_t pending_bound = 0;
+    double pending_t0 = 0;
     uint64_t host_syncs = 0;  // cudaStreamSynchronize calls of the last proof (pk_prover_host_syncs)
     ~pk_prover();  // frees every device allocation, also after a partially failed pk_prover_create
 };
@@ -224,7 +227,8 @@ struct Commitment {
 class Flow {
    public:
     Flow(pk_prover* p, pkh::Transcript* fs) : P(p), ctx(p->ctx), fs(fs), dev(fs == nullptr), M(p->mem) {}
-    int run();
+    // enqueue_only (device transcript): return as soon as everything is enqueued; the proof string's D2H is in flight
+    int run(bool enqueue_only = false);
     size_t bound_words = 0;  // upper bound of the proof string written so far (device mode: size of the final D2H)
 
    private:
@@ -590,7 +594,7 @@ int Flow::whir_prove(const WhirCfg& cfg, Commitment* cm, pk_buf* const* weights,
     return PK_OK;
 }
 
-int Flow::run() {
+int Flow::run(bool enqueue_only) {
     NvtxRange nv("prove");
     const double t_start = now_s();
     const int m = P->m, m0 = P->m0, mh = P->mh;
@@ -720,6 +724,7 @@ int Flow::run() {
         // the one host round trip of the device-transcript flow: header + proof string
         const size_t bytes = pk::DEVTS_HEADER_BYTES + 4 * std::min(bound_words, NARG_CAP_WORDS);
         PK_CUDA(ctx, cudaMemcpyAsync(M.pin_narg, M.ts, bytes, cudaMemcpyDeviceToHost, st()));
+        if (enqueue_only) return PK_OK;
     }
     PK_TRY(sync());
     if (fs && !fs->ok()) return pk::set_err(ctx, PK_ERR_INVALID_ARG, "prove: a transcript callback reported failure");
@@ -1003,12 +1008,83 @@ int pk_prover_upload_inputs(pk_prover* p, const uint64_t* witness, const pk_rand
 int pk_prover_upload_inputs_seeded(pk_prover* p, const uint64_t* witness, const uint8_t seed[32]) {
     return upload_inputs_seeded(p, witness, seed, true);
 }
+}  // extern "C"
+namespace {
+// the input uploads are asynchronous: on a failed proof make sure they no longer read the caller's arrays
+int drain_on_error(pk_prover* p, int rc) {
+    if (rc != PK_OK && p && p->ctx && p->ctx->stream) cudaStreamSynchronize(p->ctx->stream);
+    return rc;
+}
+// the finished proof string of a device-transcript run: header check + copy out of the pinned mirror
+int take_device_proof(pk_prover* p, size_t bound_words, uint8_t** out, size_t* out_len) {
+    pk_ctx* ctx = p->ctx;
+    uint32_t hdr[24];
+    std::memcpy(hdr, p->mem.pin_narg, sizeof hdr);
+    const uint32_t words = hdr[18], err = hdr[20];  // pk::DevTs: narg_words, error
+    if (err != 0 || words > bound_words)
+        return pk::set_err(ctx, PK_ERR_INTERNAL, "prove: device transcript reported error %u (%u words, bound %zu)", err, words, bound_words);
+    const size_t len = 4 * (size_t)words;
+    uint8_t* buf = (uint8_t*)std::malloc(len ? len : 1);
+    if (!buf) return pk::set_err(ctx, PK_ERR_OOM, "prove: host allocation failed");
+    std::memcpy(buf, p->mem.pin_narg + pk::DEVTS_HEADER_BYTES, len);
+    *out = buf;
+    *out_len = len;
+    return PK_OK;
+}
+int enqueue_staged(pk_prover* p) {
+    pk_ctx* ctx = p->ctx;
+    PK_CHECK(ctx, !p->host_transcript, "prove_enqueue: needs the device transcript (pk_prover_set_host_transcript(p, 0))");
+    PK_CHECK(ctx, p->staged, "prove_enqueue: inputs not staged");
+    PK_CHECK(ctx, !p->pending, "prove_enqueue: the previous proof of this prover has not been collected");
+    std::memset(p->timings, 0, sizeof p->timings);
+    p->pending_t0 = now_s();
+    Flow fl(p, nullptr);
+    PK_TRY(fl.run(true));
+    p->pending = true;
+    p->pending_bound = fl.bound_words;
+    return PK_OK;
+}
+}  // namespace
+extern "C" {
+// ---- asynchronous form of the device-transcript prover: ONE host thread keeps many proofs in flight ----
+int pk_prove_staged_enqueue(pk_prover* p) {
+    if (!p) return PK_ERR_INVALID_ARG;
+    PK_BIND(p->ctx);
+    return enqueue_staged(p);
+}
+int pk_prove_seeded_enqueue(pk_prover* p, const uint64_t* witness, const uint8_t seed[32]) {
+    if (!p) return PK_ERR_INVALID_ARG;
+    PK_BIND(p->ctx);
+    PK_CHECK(p->ctx, !p->pending, "prove_enqueue: the previous proof of this prover has not been collected");
+    PK_TRY(upload_inputs_seeded(p, witness, seed, false));
+    return drain_on_error(p, enqueue_staged(p));
+}
+int pk_prove_enqueue(pk_prover* p, const uint64_t* witness, const pk_rand* rnd) {
+    if (!p) return PK_ERR_INVALID_ARG;
+    PK_BIND(p->ctx);
+    PK_CHECK(p->ctx, !p->pending, "prove_enqueue: the previous proof of this prover has not been collected");
+    PK_TRY(upload_inputs(p, witness, rnd, false));
+    return drain_on_error(p, enqueue_staged(p));
+}
+int pk_prove_collect(pk_prover* p, uint8_t** out, size_t* out_len) {
+    if (!p) return PK_ERR_INVALID_ARG;
+    pk_ctx* ctx = p->ctx;
+    PK_BIND(ctx);
+    PK_CHECK(ctx, out && out_len, "prove_collect: null argument");
+    PK_CHECK(ctx, p->pending, "prove_collect: nothing enqueued");
+    p->pending = false;
+    PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    p->host_syncs = 1;
+    p->timings[8] = now_s() - p->pending_t0;
+    return take_device_proof(p, p->pending_bound, out, out_len);
+}
 int pk_prove_staged(pk_prover* p, uint8_t** out, size_t* out_len) {
     if (!p) return PK_ERR_INVALID_ARG;
     pk_ctx* ctx = p->ctx;
     PK_BIND(ctx);
     PK_CHECK(ctx, out && out_len, "prove: null argument");
     PK_CHECK(ctx, p->staged, "prove_staged: call pk_prover_upload_inputs first");
+    PK_CHECK(ctx, !p->pending, "prove: an enqueued proof of this prover has not been collected");
     double keep1 = p->timings[1];
     std::memset(p->timings, 0, sizeof p->timings);
     p->timings[1] = keep1;
@@ -1025,14 +1101,7 @@ int pk_prove_staged(pk_prover* p, uint8_t** out, size_t* out_len) {
     } else {  // default: the transcript lives on the device, the proof string arrives with the final synchronisation
         Flow fl(p, nullptr);
         PK_TRY(fl.run());
-        uint32_t hdr[24];
-        std::memcpy(hdr, p->mem.pin_narg, sizeof hdr);
-        const uint32_t words = hdr[18], err = hdr[20];  // pk::DevTs: narg_words, error
-        if (err != 0 || words > fl.bound_words)
-            return pk::set_err(ctx, PK_ERR_INTERNAL, "prove: device transcript reported error %u (%u words, bound %zu)", err, words,
-                               fl.bound_words);
-        src = p->mem.pin_narg + pk::DEVTS_HEADER_BYTES;
-        len = 4 * (size_t)words;
+        return take_device_proof(p, fl.bound_words, out, out_len);
     }
     uint8_t* buf = (uint8_t*)std::malloc(len ? len : 1);
     if (!buf) return pk::set_err(ctx, PK_ERR_OOM, "prove: host allocation failed");
@@ -1059,11 +1128,6 @@ int pk_prove_staged_with_transcript(pk_prover* p, const pk_transcript_vtbl* vt, 
 int pk_prove_with_transcript(pk_prover* p, const uint64_t* witness, const pk_rand* rnd, const pk_transcript_vtbl* vt, void* user) {
     PK_TRY(upload_inputs(p, witness, rnd, false));
     int rc = pk_prove_staged_with_transcript(p, vt, user);
-    if (rc != PK_OK && p && p->ctx && p->ctx->stream) cudaStreamSynchronize(p->ctx->stream);
-    return rc;
-}
-// the input uploads are asynchronous: on a failed proof make sure they no longer read the caller's arrays
-static int drain_on_error(pk_prover* p, int rc) {
     if (rc != PK_OK && p && p->ctx && p->ctx->stream) cudaStreamSynchronize(p->ctx->stream);
     return rc;
 }

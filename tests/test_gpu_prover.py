@@ -103,3 +103,32 @@ def test_hot_column_long_rows(ctx, orc):
     buf = np.frombuffer(got, dtype=np.uint8)
     assert orc.orc_verify(ctypes.byref(cs), buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(got)), 2) == 0
     pr.close()
+
+
+def test_enqueue_collect_pipeline(ctx, orc):
+    """asynchronous form: one host thread keeps several provers busy; every collected proof equals the oracle's"""
+    import provekit_b200 as pk
+    rs = [SyntheticR1CS(300 + 50 * i, 400, seed=70 + i) for i in range(3)]
+    ctxs = [pk.Context(0) for _ in rs]
+    provers = [pk.Prover(c, as_dict(r)) for c, r in zip(ctxs, rs)]
+    expected = [oracle_prove(orc, r) for r in rs]
+    for round_ in range(2):
+        for p, r in zip(provers, rs):
+            p.enqueue(r.witness, r.randomness())
+        for p, e in zip(provers, expected):
+            assert p.collect() == e
+            assert p.host_syncs == 1
+    # misuse: collect without enqueue, enqueue twice, and the host-transcript mode
+    with pytest.raises(pk.PkError):
+        provers[0].collect()
+    provers[0].enqueue(rs[0].witness, rs[0].randomness())
+    with pytest.raises(pk.PkError):
+        provers[0].enqueue(rs[0].witness, rs[0].randomness())
+    assert provers[0].collect() == expected[0]
+    provers[1].set_host_transcript(True)
+    with pytest.raises(pk.PkError):
+        provers[1].enqueue(rs[1].witness, rs[1].randomness())
+    for p in provers:
+        p.close()
+    for c in ctxs:
+        c.close()
