@@ -196,9 +196,15 @@ int pk_whir_sumcheck_round_sharded(pk_ctx *ctx, const pk_buf *p_in, const pk_buf
                                    int log_n, const uint64_t *fold_or_null, uint64_t out3[12]);
 
 /* ---- seam: WhirR1CSProver::prove (provekit/prover/src/whir_r1cs.rs:42-100) --------------------
- * The whole hot path driven by this library's own host-side Fiat-Shamir transcript
- * (provekit_b200/csrc/host/).  R1CS in the reference's interned-CSR form
- * (provekit/common/src/sparse_matrix.rs:19-26, interner.rs). */
+ * The whole hot path.  Two ways to drive it:
+ *   pk_prove_with_transcript  THE DROP-IN: every Fiat-Shamir operation is a callback into the host's own spongefish
+ *                             ProverState, so the proof bytes are the reference's by construction.
+ *   pk_prove / pk_prove_seeded / *_enqueue   the same flow over this library's IN-TREE restatement of the sponge
+ *                             (on the device by default).  spongefish is not vendored in the reference and its challenge
+ *                             derivation could not be pinned here (DESIGN.md "parity unpinned"): these entry
+ *                             points are for measurement and for self-contained use with this repo's verifier; a reference
+ *                             or gnark verifier is only guaranteed to accept proofs made through the callback entry point.
+ * R1CS in the reference's interned-CSR form (provekit/common/src/sparse_matrix.rs:19-26, interner.rs). */
 typedef struct {
     uint64_t num_rows, num_cols, nnz;
     const uint64_t *row_start; /* num_rows offsets into col/val */

@@ -942,6 +942,7 @@ int upload_inputs(pk_prover* p, const uint64_t* witness, const pk_rand* rnd, boo
     pk_ctx* ctx = p->ctx;
     PK_BIND(ctx);
     PK_CHECK(ctx, witness && rnd, "upload_inputs: null argument");
+    PK_CHECK(ctx, !p->pending, "upload_inputs: an enqueued proof still reads the staged inputs (pk_prove_collect first)");
     PK_CHECK(ctx, rnd->mask_w && rnd->g_w && rnd->blind && rnd->mask_h && rnd->g_h, "upload_inputs: null randomness");
     const size_t half = (size_t)1 << (p->m - 1), N = (size_t)1 << p->m;
     const size_t halfh = (size_t)1 << (p->mh - 1), Nh = (size_t)1 << p->mh;
@@ -976,6 +977,7 @@ int upload_inputs_seeded(pk_prover* p, const uint64_t* witness, const uint8_t se
     pk_ctx* ctx = p->ctx;
     PK_BIND(ctx);
     PK_CHECK(ctx, witness && seed, "upload_inputs_seeded: null argument");
+    PK_CHECK(ctx, !p->pending, "upload_inputs: an enqueued proof still reads the staged inputs (pk_prove_collect first)");
     const size_t half = (size_t)1 << (p->m - 1), N = (size_t)1 << p->m;
     const size_t halfh = (size_t)1 << (p->mh - 1), Nh = (size_t)1 << p->mh;
     const size_t nb = 4 * (size_t)p->m0;
