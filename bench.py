@@ -4,7 +4,8 @@
 A "step" is ONE full proof: WhirR1CSProver::prove on a synthetic satisfiable R1CS with the shapes of the
 reference's poseidon-rounds fixture (configs[1]), i.e. witness commit (wavelet, RS-encode NTT,
 Skyscraper Merkle tree), zk-sumcheck, blinding WHIR, R1CS weights, witness WHIR (sumchecks, round commits,
-PoW grinding, STIR openings) with the Fiat-Shamir transcript on the host.
+PoW grinding, STIR openings) with the Fiat-Shamir transcript kept on the device (csrc/devts.cuh): one host thread per GPU
+enqueues whole proofs (pk_prove_*_enqueue) and collects the proof strings (pk_prove_collect).
 
   value  proofs/s with the proof's inputs (witness, masks) already resident in HBM  (pk_prove_staged)
   e2e    proofs/s through the C-ABI call with HOST (pinned) buffers: H2D of the witness (+ a 32-byte seed; the
@@ -276,10 +277,10 @@ def main():
     keep = []
     witness, t_ = pin(r1cs["witness"])
     keep.append(t_)
-    rnd_p = {}
+    rnd_p, rnd_t = {}, {}
     for k, v in rnd.items():
-        rnd_p[k], t_ = pin(v)
-        keep.append(t_)
+        rnd_p[k], rnd_t[k] = pin(v)
+        keep.append(rnd_t[k])
 
     # proofs in flight per GPU: fixed (each has its own ctx / stream / host thread); the K..K_region proofs of a timed region
     # are handed out dynamically, so the count need not divide K
@@ -371,6 +372,15 @@ def main():
     barrier()
     if sampler:
         sampler.start()
+    # (a0) one proof in flight, no profiling hooks: the single-proof latency
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prover.prove_staged()
+    e0.record(stream)
+    for _ in range(args.steps):
+        prover.prove_staged()
+    e1.record(stream)
+    ctx.sync()
+    latency_ms = e0.elapsed_time(e1) / args.steps
     # (a) one proof at a time with per-kernel CUDA events: kernel durations for the roofline
     launches0 = ctx.launches
     ctx._chk(ctx.L.pk_profile_begin(ctx.h))
@@ -409,6 +419,7 @@ def main():
     dev_ms, dev_reps = median(reps), [round(x, 3) for x in reps]
     barrier()
     single_ms = max_over_ranks(single_ms)
+    latency_ms = max_over_ranks(latency_ms)
 
     # ---- e2e arm: host buffers in, transcript out, every step ----
     run_seeded(n_fl)
@@ -424,7 +435,18 @@ def main():
     e2e_detail = {"device_ms": e2e_dev, "wall_ms": e2e_wall, "repetitions_ms": [round(r[0], 3) for r in reps],
                   "host_stage_s_last_proof": dict(zip(
         ["commit", "h2d", "zk_sumcheck", "whir_sumcheck", "pow", "open", "spmv_weights", "other", "total"], [round(x, 5) for x in prover.timings()]))}
-    # the same with the masks as host arrays (the reference's API semantics: the host owns the randomness), one repetition
+    # the same with the masks as host arrays (the reference's API semantics: the host owns the randomness), one repetition.
+    # 128 MB cross PCIe per proof on this path; the link rate measured here (pinned H2D of g_w, 64 MiB, 4 times) bounds it
+    gw_pin = rnd_t["g_w"].view(torch.int64).reshape(-1)
+    gw_dev = torch.empty_like(gw_pin, device=f"cuda:{local_rank}")
+    gw_dev.copy_(gw_pin, non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        gw_dev.copy_(gw_pin, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_gbs = 4 * gw_dev.numel() * 8 / (time.perf_counter() - t0) / 1e9
+    del gw_dev
     run_masks(n_fl)
     barrier()
     hm_steps = max(args.steps, 4 * n_fl)
@@ -462,13 +484,16 @@ def main():
                                     f"K = {args.steps}, at least {MIN_REGION_STEPS}: >= 1 s per repetition), {n_fl} proofs in flight handed "
                                     "out dynamically; CUDA events (e2e additionally bounded below by host wall clock), max over ranks")
         line["timed_steps_per_repetition"] = region
-        line.update({"value": value, "ms_per_step": dev_ms / region, "ms_per_step_one_in_flight": single_ms / args.steps,
+        line.update({"value": value, "ms_per_step": dev_ms / region, "ms_per_step_one_in_flight": latency_ms,
+                     "ms_per_step_one_in_flight_profiled": single_ms / args.steps,
                      "gpu_launches": int(launches), "clocks": clocks,
                      "e2e": {"value": aggregate_throughput(region, world, e2e_ms), "unit": "proofs/s", "h2d_bytes_per_step": int(h2d),
                              "d2h_bytes_per_step": int(d2h)},
                      "value_repetitions_ms": dev_reps, "e2e_detail": e2e_detail,
                      "e2e_host_masks": {"value": aggregate_throughput(hm_steps, world, hm_ms), "unit": "proofs/s",
-                                        "h2d_bytes_per_step": int(h2d_host_masks), "d2h_bytes_per_step": int(d2h)}})
+                                        "h2d_bytes_per_step": int(h2d_host_masks), "d2h_bytes_per_step": int(d2h),
+                                        "pcie_h2d_gbs_measured": round(h2d_gbs, 2),
+                                        "pcie_bound_proofs_per_s": round(h2d_gbs * 1e9 / h2d_host_masks, 1)}})
         # roofline of the dominant kernel: Merkle leaf hashing of the witness commitment (L = 2^(m-3) leaves of 32)
         L = 1 << (m + 1 - 4)
         leaf_bytes = 32 * (L * 32 + L)           # read L*w elements, write L digests (leaf level of K2)
@@ -485,22 +510,27 @@ def main():
                             "frac": ach / peak if ach else None, "traffic": traffic, "algorithmic_bytes": leaf_bytes,
                             "ms_per_launch": leaf_ms, "gcompress_per_s": n_compress / (leaf_ms / 1e3) / 1e9 if leaf_ms > 0 else None,
                             "class_ms_per_proof": ms_cls[1] / args.steps,
-                            "note": "integer-ALU bound (about 2.6k IMAD.WIDE per 32 B hashed): the HBM fraction is low by "
+                            "note": "integer-ALU bound (about 1.3k IMAD.WIDE per 32 B hashed: 14 squarings of 92): the HBM fraction is low by "
                                     "construction; DESIGN.md gives the modmul/s ceiling this kernel is measured against"}
         names = ["rs_encode_ntt", "merkle_leaves", "merkle_upper", "zk_sumcheck", "whir_sumcheck", "wavelet", "pow", "other"]
         line["kernel_ms_per_proof"] = {names[i]: ms_cls[i] / args.steps for i in range(8)}
         ntt_ms = ms_cls[0] / args.steps
         if ntt_ms > 0:
             nb = wl.rs_encode_bytes(m, mh)
-            ntt_traffic = None
+            ntt_traffic, ntt_scope = None, None
             try:
-                ntt_traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["rs_encode"]["dram_bytes_per_proof"]
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["rs_encode"]
+                # the ncu capture covers the witness commitment's two polynomials; the WHIR round commitments (the rest of the
+                # proof's encodes) run the same kernel, so the measured traffic ratio is applied to the proof's algorithmic bytes
+                ntt_traffic = int(round(nb * tj["dram_bytes"] / tj["algorithmic_bytes"]))
+                ntt_scope = (f"ncu: {tj['dram_bytes']} B for {tj['algorithmic_bytes']} algorithmic B ({tj['scope']}); "
+                             "scaled to the algorithmic bytes of all encodes of one proof")
             except Exception:
                 pass
-            line["roofline_ntt"] = {"kernel": "RS-encode NTT passes, all commitments of one proof", "bound": "hbm",
+            line["roofline_ntt"] = {"kernel": "RS-encode NTT passes (k_ntt_r8, TMA-staged radix-8), all commitments of one proof", "bound": "hbm",
                                     "achieved": nb / (ntt_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                                    "frac": nb / (ntt_ms / 1e3) / 1e9 / peak, "traffic": ntt_traffic, "algorithmic_bytes": nb,
-                                    "ms_per_proof": ntt_ms}
+                                    "frac": nb / (ntt_ms / 1e3) / 1e9 / peak, "traffic": ntt_traffic, "traffic_scope": ntt_scope,
+                                    "algorithmic_bytes": nb, "ms_per_proof": ntt_ms}
         if sharded_info is not None:
             line["sharded"] = sharded_info
         line["host_stage_s_last_proof"] = dict(zip(["commit", "h2d", "zk_sumcheck", "whir_sumcheck", "pow", "open", "spmv_weights",
