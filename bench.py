@@ -449,7 +449,7 @@ def main():
     del gw_dev
     run_masks(n_fl)
     barrier()
-    hm_steps = max(args.steps, 4 * n_fl)
+    hm_steps = region
     hm_ms, hm_wall, _ = run_masks(hm_steps)
     barrier()
     hm_ms = max_over_ranks(max(hm_ms, hm_wall))
