@@ -245,23 +245,34 @@ class ShardedCommit:
 
     def commit(self) -> np.ndarray:
         """-> canonical root (4 limbs), identical on every rank and to the single-GPU pk_commit_batch root"""
+        import time
         ctx = self.ctx
+        t = [time.perf_counter()]
         for b, cs in self.groups.items():
             ctx.rs_encode_sharded(self.polys[b], self.log_n, self.rate, min(cs), len(cs), self.peers, self.w, 16 * b)
         ctx.sync()
+        t.append(time.perf_counter())
         if self.world > 1:
             self.dist.barrier()  # a rank's rows are complete only after ALL peers finished storing into them
+        t.append(time.perf_counter())
         ctx.merkle_build(self.leaves, self.per, self.w, self.nodes)
         sub = self.nodes.download(1, 1)  # canonical sub-tree root
+        t.append(time.perf_counter())
         if self.world == 1:
-            return ctx.merkle_combine_roots(sub)
-        import torch
-        mine = torch.from_numpy(sub.view(np.int64).reshape(-1).copy())
-        if self.coll_device is not None:
-            mine = mine.to(self.coll_device)
-        out = torch.empty(self.world * 4, dtype=torch.int64, device=mine.device)
-        self.dist.all_gather_into_tensor(out, mine)
-        return ctx.merkle_combine_roots(out.cpu().numpy().view(np.uint64).reshape(self.world, 4))
+            root = ctx.merkle_combine_roots(sub)
+        else:
+            import torch
+            mine = torch.from_numpy(sub.view(np.int64).reshape(-1).copy())
+            if self.coll_device is not None:
+                mine = mine.to(self.coll_device)
+            out = torch.empty(self.world * 4, dtype=torch.int64, device=mine.device)
+            self.dist.all_gather_into_tensor(out, mine)
+            root = ctx.merkle_combine_roots(out.cpu().numpy().view(np.uint64).reshape(self.world, 4))
+        t.append(time.perf_counter())
+        # host-clock phases of the last commit on this rank: encode + peer stores, barrier, sub-tree, roots
+        self.phases_ms = {k: round((t[i + 1] - t[i]) * 1e3, 3) for i, k in
+                          enumerate(("encode_and_exchange", "barrier", "merkle_subtree", "allgather_and_top"))}
+        return root
 
     def close(self):
         for p in self.opened:
@@ -287,6 +298,74 @@ def bench_sharded(pk, ctx, dist, rank: int, world: int, coll_device, log_n_commi
 
     barrier = barrier or (lambda: dist.barrier() if dist is not None else None)
     max_over_ranks = max_over_ranks or (lambda x: x)
+
+    nv_note = []
+
+    def nvml_handle():
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(torch.cuda.current_device())
+        return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+
+    def nvlink_tx_bytes():
+        """NVLink payload bytes this rank's GPU has transmitted so far (NVML counters summed over its links, KiB
+        granularity; `nvidia-smi nvlink -gt d` as the fallback)."""
+        try:
+            nv, h = nvml_handle()
+            total, seen = 0, 0
+            for link in range(18):
+                try:
+                    v = nv.nvmlDeviceGetFieldValues(h, [(nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, link)])[0]
+                except Exception:
+                    continue
+                if v.nvmlReturn == 0:
+                    total += int(v.value.ullVal) * 1024
+                    seen += 1
+            if seen:
+                return total
+        except Exception as e:  # counters are evidence, never a reason to lose the line
+            nv_note.append(f"nvml: {type(e).__name__}: {e}")
+        try:
+            import re
+            import subprocess
+            import torch
+            pr = torch.cuda.get_device_properties(torch.cuda.current_device())
+            bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            o = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", bus], capture_output=True, text=True, timeout=20).stdout
+            vals = [int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", o)]
+            if vals:
+                return sum(vals) * 1024
+            nv_note.append("nvidia-smi nvlink -gt d: no Data Tx lines")
+        except Exception as e:
+            nv_note.append(f"nvidia-smi: {type(e).__name__}: {e}")
+        return None
+
+    def p2p_gbs():
+        """rank 0 -> rank 1 device-to-device rate through NCCL send/recv of 256 MiB (what the peer stores ride on)"""
+        try:
+            import torch
+            if dist is None or world < 2 or coll_device is None:
+                return None
+            buf = torch.empty(1 << 28, dtype=torch.uint8, device=coll_device)
+            best = None
+            for _ in range(3):
+                torch.cuda.synchronize()
+                barrier()
+                t0 = time.perf_counter()
+                if rank == 0:
+                    dist.send(buf, 1)
+                elif rank == 1:
+                    dist.recv(buf, 0)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            del buf
+            return round((1 << 28) / best / 1e9, 1)
+        except Exception as e:
+            nv_note.append(f"p2p probe: {type(e).__name__}: {e}")
+            return None
+
     rng = np.random.default_rng(seed)
     polys_host = [rand_fr(rng, 1 << log_n_commit) for _ in range(2)]
     polys = [ctx.upload(p) for p in polys_host]
@@ -294,12 +373,22 @@ def bench_sharded(pk, ctx, dist, rank: int, world: int, coll_device, log_n_commi
     for _ in range(warmup):
         root = sc.commit()
     ctx.sync()
-    barrier()
+    nv0 = nvlink_tx_bytes()
+    barrier()  # after the counter read: its duration differs per rank and would show up as waiting time in the first commit
     t0 = time.perf_counter()
     for _ in range(steps):
         root = sc.commit()
     ctx.sync()
     commit_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+    nv1 = nvlink_tx_bytes()
+    phases = getattr(sc, "phases_ms", None)
+    # the fused exchange: every rank stores (world - 1) / world of ITS columns' codeword share into peer memory
+    codeword_bytes = 2 * 32 * (1 << (log_n_commit + 1))
+    nvlink = {"tx_bytes_per_commit_rank0": None if nv0 is None or nv1 is None else (nv1 - nv0) // steps,
+              "expected_payload_bytes_per_rank": codeword_bytes // world * (world - 1) // world,
+              "p2p_gbs_rank0_to_rank1": p2p_gbs(), "notes": nv_note,
+              "source": "NVML NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX summed over the active links of rank 0's GPU, around the timed "
+                        "commits; p2p rate = NCCL send/recv of 256 MiB"}
     sc.close()
     barrier()
     one_ms, root_ok = None, None
@@ -404,7 +493,7 @@ def bench_sharded(pk, ctx, dist, rank: int, world: int, coll_device, log_n_commi
             "root_matches_single_gpu": root_ok, "commit_alg_gbs": alg / commit_ms / 1e6,
             "zk_sumcheck_ms": zk_ms, "zk_sumcheck_ms_1gpu": zk1_ms, "whir_sumcheck_ms": wh_ms, "whir_sumcheck_ms_1gpu": wh1_ms,
             "sumcheck_messages_match_single_gpu": msgs_ok,
-            "exchange": "ipc-peer-store",
+            "commit_phases_ms_rank0": phases, "exchange": "ipc-peer-store", "nvlink": nvlink,
             "exchange_detail": "codeword transpose fused into the last NTT pass as NVLink peer stores into CUDA-IPC mapped leaf blocks; "
                                "sub-tree roots all-gathered (32 B per rank); sumcheck round messages exchanged by a one-warp kernel over "
                                "peer mailboxes and summed on the device",
