@@ -427,11 +427,15 @@ static int rs_encode_raw(pk_ctx* ctx, const void* coeffs, int log_n, int log_inv
     const int L = log_n - fold, logM = L + log_inv_rate;
     PK_TRY(ensure_twiddles(ctx, logM));
     PK_TRY(ensure_scratch(ctx, (size_t)1 << (log_n + log_inv_rate)));
-    // k_ntt_r8 pays when a column fits two passes of full tiles (2^8..2^9 points x 4 columns, 128-256 threads); a third pass
-    // means 2^6..2^7-point tiles and 32-64-thread CTAs: measured 3.59 ms against 3.13 ms for the radix-2 kernel at
-    // log_n = 23 (L = 19), so longer columns stay on k_ntt_pass like the tiny ones
-    const bool use_r8 = L >= NTT8_MIN_L && L <= 2 * NTT8_MAX_S &&
-                        !(std::getenv("PK_NTT_LEGACY") && std::getenv("PK_NTT_LEGACY")[0] == '1');
+    // Kernel choice (measured on B200, profiles/r02_ntt_kernel_choice.jsonl): the TMA-staged radix-8 kernel runs the columns of
+    // the witness commitment (L = 17, 18: two passes of full 2^8..2^9-point tiles; within 2 % of the radix-2 kernel's time at
+    // 58 % of its DRAM traffic).  Shorter columns (32-128-thread CTAs) and a third pass (L >= 19) are 5-15 % slower than the
+    // register-staged radix-2 kernel, which keeps them.  PK_NTT_KERNEL=r8 | radix2 forces one kernel (tests, A/B runs).
+    const char* force = std::getenv("PK_NTT_KERNEL");
+    const bool legacy_env = std::getenv("PK_NTT_LEGACY") && std::getenv("PK_NTT_LEGACY")[0] == '1';
+    bool use_r8 = L >= 17 && L <= 2 * NTT8_MAX_S;
+    if (force && force[0] == 'r' && force[1] == '8') use_r8 = L >= NTT8_MIN_L;
+    if ((force && force[0] == 'r' && force[1] == 'a') || legacy_env) use_r8 = false;
     if (!use_r8) {  // tiny and very long transforms: the register-staged radix-2 kernel
         ProfScope ps(ctx, PROF_NTT);
         ctx->launches += launch_rs_encode(ctx->stream, coeffs, log_n, log_inv_rate, fold, leaves, leaf_stride, col_offset,

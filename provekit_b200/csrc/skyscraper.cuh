@@ -35,43 +35,41 @@ __constant__ uint32_t SKY_RC[18][8] = {
 };
 
 // per-byte sbox on 4 packed bytes (bar.rs:40-65): rotl1(v ^ (~rotl1(v) & rotl2(v) & rotl3(v)))
+// On the ALU pipe only.  A byte-wise rotate-left by k is the 32-bit rotate-left by k with the k low bits of
+// every byte replaced by those of the 32-bit rotate-right by 8-k (the bits that wrapped inside the byte): two funnel shifts
+// and ONE three-input LOP3 (bit select under a constant mask).  The plain shift-and-mask form costs the multiplier pipe four
+// instructions per word (ptxas lowers the left shifts to IMAD.SHL / IMAD.IADD), and the multiplier pipe is what bounds the
+// hash; this form is 8 SHF + 6 LOP3 and leaves that pipe alone.
+template <int K>
+__device__ __forceinline__ uint32_t rotl_bytes(uint32_t v) {
+    const uint32_t low = (0xffu >> (8 - K)) * 0x01010101u;
+    const uint32_t a = __funnelshift_l(v, v, K), b = __funnelshift_r(v, v, 8 - K);
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(d) : "r"(a), "r"(b), "r"(low));  // (a & ~low) | (b & low)
+    return d;
+}
 __device__ __forceinline__ uint32_t sbox4(uint32_t v) {
-    uint32_t t1 = ((v & 0x80808080u) >> 7) | ((v & 0x7f7f7f7fu) << 1);
-    uint32_t t2 = ((v & 0xc0c0c0c0u) >> 6) | ((v & 0x3f3f3f3fu) << 2);
-    uint32_t t3 = ((v & 0xe0e0e0e0u) >> 5) | ((v & 0x1f1f1f1fu) << 3);
-    uint32_t tmp = (~t1 & t2 & t3) ^ v;
-    return ((tmp & 0x80808080u) >> 7) | ((tmp & 0x7f7f7f7fu) << 1);
+    const uint32_t t1 = rotl_bytes<1>(v), t2 = rotl_bytes<2>(v), t3 = rotl_bytes<3>(v);
+    return rotl_bytes<1>((~t1 & t2 & t3) ^ v);
 }
 
+// q * p for q = 0..5 (skyscraper/core/src/constants.rs:9-16 MODULUS[0..5]) as 32-bit limbs
+__constant__ uint32_t SKY_QP[6][8] = {
+    {0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u},
+    {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u},
+    {0xe0000002u, 0x87c3eb27u, 0xf372e122u, 0x5067d090u, 0x0302b0bau, 0x70a08b6du, 0xc2634053u, 0x60c89ce5u},
+    {0xd0000003u, 0xcba5e0bbu, 0x6d2c51b3u, 0x789bb8d9u, 0x84840917u, 0x28f0d123u, 0xa394e07du, 0x912ceb58u},
+    {0xc0000004u, 0x0f87d64fu, 0xe6e5c245u, 0xa0cfa121u, 0x06056174u, 0xe14116dau, 0x84c680a6u, 0xc19139cbu},
+    {0xb0000005u, 0x5369cbe3u, 0x609f32d6u, 0xc903896au, 0x8786b9d1u, 0x99915c90u, 0x65f820d0u, 0xf1f5883eu},
+};
 // value < 2^256 -> [0, p): q = floor(top limb / (P7+1)) in 0..5, subtract q*p, one conditional subtract
 // (the reduce_partial idea of skyscraper/core/src/reduce.rs:33-40 followed by reduce_1 :21-29)
 __device__ __forceinline__ fr sky_reduce(const fr& x) {
     uint32_t q = x.v[7] / (PK_P7 + 1u);
     uint32_t qp[8];
-    uint32_t c;
-    // q*p: q <= 5 so every product fits well inside 64 bits; one chain of wide multiplies
-    asm("{\n\t"
-        ".reg .u32 hi;\n\t"
-        "mul.lo.u32 %0, %9, %10;\n\t"
-        "mul.hi.u32 hi, %9, %10;\n\t"
-        "mad.lo.cc.u32 %1, %9, %11, hi;\n\t"
-        "madc.hi.u32 hi, %9, %11, 0;\n\t"
-        "mad.lo.cc.u32 %2, %9, %12, hi;\n\t"
-        "madc.hi.u32 hi, %9, %12, 0;\n\t"
-        "mad.lo.cc.u32 %3, %9, %13, hi;\n\t"
-        "madc.hi.u32 hi, %9, %13, 0;\n\t"
-        "mad.lo.cc.u32 %4, %9, %14, hi;\n\t"
-        "madc.hi.u32 hi, %9, %14, 0;\n\t"
-        "mad.lo.cc.u32 %5, %9, %15, hi;\n\t"
-        "madc.hi.u32 hi, %9, %15, 0;\n\t"
-        "mad.lo.cc.u32 %6, %9, %16, hi;\n\t"
-        "madc.hi.u32 hi, %9, %16, 0;\n\t"
-        "mad.lo.cc.u32 %7, %9, %17, hi;\n\t"
-        "madc.hi.u32 %8, %9, %17, 0;\n\t"
-        "}"
-        : "=r"(qp[0]), "=r"(qp[1]), "=r"(qp[2]), "=r"(qp[3]), "=r"(qp[4]), "=r"(qp[5]), "=r"(qp[6]), "=r"(qp[7]),
-          "=r"(c)
-        : "r"(q), "r"(PK_P0), "r"(PK_P1), "r"(PK_P2), "r"(PK_P3), "r"(PK_P4), "r"(PK_P5), "r"(PK_P6), "r"(PK_P7));
+    // the multiple comes from constant memory (8 LDC) instead of 8 wide multiplies: the multiplier pipe bounds the hash
+#pragma unroll
+    for (int k = 0; k < 8; k++) qp[k] = SKY_QP[q][k];
     fr d;
     asm("sub.cc.u32 %0, %8, %16;\n\t"
         "subc.cc.u32 %1, %9, %17;\n\t"

@@ -89,11 +89,15 @@ def test_wavelet_vs_oracle(ctx, orc, log_n):
     buf.free()
 
 
-# column length 2^L, L = log_n - 4: L < 7 runs the register-staged radix-2 kernel, L >= 7 the TMA-staged radix-8 kernel with one
-# pass (L <= 9: 11, 12, 13), two (17 -> 7+6, 18 -> 7+7, 20 -> 8+8, 21 -> 9+8, 22 -> 9+9) or three (23 -> 7+6+6)
+# column length 2^L, L = log_n - 4.  kernel "r8": the TMA-staged radix-8 kernel for every L >= 7 — one pass (L <= 9: 11, 12, 13),
+# two (17 -> 7+6, 18 -> 7+7, 20 -> 8+8, 21 -> 9+8, 22 -> 9+9) or three (23 -> 7+6+6); L < 7 always runs the radix-2 kernel.
+# kernel "radix2": the register-staged radix-2 kernel everywhere.  The product picks r8 for L = 17, 18 and radix-2 otherwise
+# (pkwhir.cu rs_encode_raw), so every shape below is covered on the kernel the product uses and on the other one.
+@pytest.mark.parametrize("kernel", ["r8", "radix2"])
 @pytest.mark.parametrize("log_n,rate", [(4, 1), (4, 4), (5, 13), (9, 10), (10, 3), (11, 1), (11, 0), (12, 2), (13, 7), (14, 1), (17, 4),
                                         (18, 1), (20, 1), (21, 1), (22, 1), (23, 1)])
-def test_rs_encode_vs_oracle(ctx, orc, log_n, rate):
+def test_rs_encode_vs_oracle(ctx, orc, log_n, rate, kernel, monkeypatch):
+    monkeypatch.setenv("PK_NTT_KERNEL", kernel)
     a = rng_fr(1000 + log_n, 1 << log_n)
     rows = 1 << (log_n + rate - 4)
     exp = np.zeros((rows * 16, 4), np.uint64)
