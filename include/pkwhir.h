@@ -124,6 +124,17 @@ int pk_commit_open(pk_ctx *ctx, const pk_commitment *c, const uint64_t *sorted_i
                    uint64_t *leaves_out, uint64_t *sibling_out, uint64_t *prefix_len_out,
                    uint64_t *suffix_out, uint64_t *suffix_len_out, size_t suffix_cap);
 
+/* the two halves of pk_commit_open, for a SHARDED opening ("pk_commit_open routes each queried index to its owner
+ * rank"): every rank opens ITS rows with pk_commit_open_paths on a view of its leaf block and sub-tree (pk_commit_wrap, local
+ * row indexes), the uncompressed paths are gathered in rank order, extended by the levels above the sub-trees (computed from
+ * the all-gathered sub-roots) and compressed once with pk_multipath_build.  paths[q][level]: level 0 = sibling leaf digest,
+ * level depth-1 = the sibling below the root; canonical digests. */
+int pk_commit_wrap(pk_ctx *ctx, const pk_buf *leaves, const pk_buf *nodes, size_t num_leaves, size_t leaf_width, pk_commitment **out);
+int pk_commit_open_paths(pk_ctx *ctx, const pk_commitment *c, const uint64_t *sorted_idx, size_t n_idx, uint64_t *leaves_out,
+                         uint64_t *paths_out);
+int pk_multipath_build(pk_ctx *ctx, const uint64_t *paths, size_t n_idx, int depth, uint64_t *sibling_out, uint64_t *prefix_len_out,
+                       uint64_t *suffix_out, uint64_t *suffix_len_out, size_t suffix_cap);
+
 /* ---- univariate / multilinear helpers used by commit_batch and Prover::prove [whir] ---------- */
 /* OOD answer: coefficient vector evaluated at (z^(2^(n-1)),..,z^2,z) = Horner at z */
 int pk_eval_univariate(pk_ctx *ctx, const pk_buf *coeffs, size_t n, const uint64_t z[4], uint64_t out[4]);

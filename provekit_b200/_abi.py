@@ -84,6 +84,9 @@ def lib() -> ctypes.CDLL:
         "pk_rs_encode_sharded": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, POINTER(vp), c_int, sz, sz]),
         "pk_merkle_combine_roots": (c_int, [vp, u64p, c_int, u64p]),
         "pk_commit_open": (c_int, [vp, vp, u64p, sz, u64p, u64p, u64p, u64p, u64p, sz]),
+        "pk_commit_wrap": (c_int, [vp, vp, vp, sz, sz, POINTER(vp)]),
+        "pk_commit_open_paths": (c_int, [vp, vp, u64p, sz, u64p, u64p]),
+        "pk_multipath_build": (c_int, [vp, u64p, sz, c_int, u64p, u64p, u64p, u64p, sz]),
         "pk_eval_univariate": (c_int, [vp, vp, sz, u64p, u64p]),
         "pk_eval_univariate_batch": (c_int, [vp, POINTER(vp), c_int, sz, u64p, u64p]),
         "pk_multi_dot": (c_int, [vp, POINTER(vp), c_int, POINTER(vp), c_int, sz, u64p]),

@@ -101,6 +101,16 @@ class Commitment:
             pos += int(k)
         return leaves.reshape(n, self.leaf_width, 4), sib, pre, sufs
 
+    def open_paths(self, sorted_indexes):
+        """STIR answers + UNCOMPRESSED authentication paths (pk_commit_open_paths): (leaves (n,w,4) Montgomery,
+        paths (n, depth, 4) canonical, level 0 = sibling leaf digest .. level depth-1 = sibling below the root)."""
+        idx = np.ascontiguousarray(sorted_indexes, dtype=np.uint64)
+        n = len(idx)
+        leaves = np.empty((n * self.leaf_width, 4), np.uint64)
+        paths = np.empty((n * max(self.depth, 1), 4), np.uint64)
+        self.ctx._chk(self.ctx.L.pk_commit_open_paths(self.ctx.h, self.h, _p(idx), n, _p(leaves), _p(paths)))
+        return leaves.reshape(n, self.leaf_width, 4), paths[:n * self.depth].reshape(n, self.depth, 4)
+
     def free(self):
         if self.h:
             self.ctx.L.pk_commit_free(self.ctx.h, self.h)
@@ -168,6 +178,28 @@ class Context:
         arr = (c_void_p * len(peer_ptrs))(*[c_void_p(p) for p in peer_ptrs])
         self._chk(self.L.pk_rs_encode_sharded(self.h, coeffs.h, log_n, log_inv_rate, fold, col_first, n_cols, arr,
                                               len(peer_ptrs), leaf_stride, col_offset))
+
+    def commit_wrap(self, leaves: Buffer, nodes: Buffer, num_leaves: int, leaf_width: int) -> Commitment:
+        """a shard's leaf block + sub-tree as a (non-owning) Commitment: open() / open_paths() with local row indexes"""
+        h = c_void_p()
+        self._chk(self.L.pk_commit_wrap(self.h, leaves.h, nodes.h, num_leaves, leaf_width, byref(h)))
+        return Commitment(self, h, None)
+
+    def multipath_build(self, paths):
+        """(n, depth, 4) uncompressed paths -> ark MultiPath pieces (siblings (n,4), prefix_lens, suffixes), pk_multipath_build"""
+        paths = np.ascontiguousarray(paths, dtype=np.uint64)
+        n, depth = paths.shape[0], paths.shape[1]
+        sib = np.empty((n, 4), np.uint64)
+        pre = np.empty(n, np.uint64)
+        slen = np.empty(n, np.uint64)
+        cap = max(n * depth, 1)
+        suf = np.empty((cap, 4), np.uint64)
+        self._chk(self.L.pk_multipath_build(self.h, _p(paths), n, depth, _p(sib), _p(pre), _p(suf), _p(slen), cap))
+        sufs, pos = [], 0
+        for k in slen:
+            sufs.append(suf[pos:pos + int(k)].copy())
+            pos += int(k)
+        return sib, pre, sufs
 
     def merkle_combine_roots(self, roots) -> np.ndarray:
         r = np.ascontiguousarray(roots, dtype=np.uint64).reshape(-1, 4)

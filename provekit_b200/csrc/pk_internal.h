@@ -69,6 +69,7 @@ struct pk_commitment {
     size_t L = 0, w = 0;
     int depth = 0;
     bool canonical_leaves = false;  // leaves hold canonical integers instead of Montgomery-form elements
+    bool owns = true;               // false: a view over the caller's buffers (pk_commit_wrap), freed by the caller
 };
 
 namespace pk {

@@ -602,6 +602,10 @@ int pk_commit_batch(pk_ctx* ctx, const pk_buf* const* coeffs, int batch, int log
 void pk_commit_free(pk_ctx* ctx, pk_commitment* c) {
     PK_BIND(ctx);
     if (!c) return;
+    if (!c->owns) {
+        delete c;
+        return;
+    }
     if (ctx && ctx->stream) {
         if (c->leaves) cudaFreeAsync(c->leaves, ctx->stream);
         if (c->nodes) cudaFreeAsync(c->nodes, ctx->stream);
@@ -614,12 +618,31 @@ void pk_commit_free(pk_ctx* ctx, pk_commitment* c) {
 size_t pk_commit_num_leaves(const pk_commitment* c) { return c ? c->L : 0; }
 size_t pk_commit_leaf_width(const pk_commitment* c) { return c ? c->w : 0; }
 
-int pk_commit_open(pk_ctx* ctx, const pk_commitment* c, const uint64_t* sorted_idx, size_t n_idx, uint64_t* leaves_out,
-                   uint64_t* sibling_out, uint64_t* prefix_len_out, uint64_t* suffix_out, uint64_t* suffix_len_out,
-                   size_t suffix_cap) {
+// A shard's leaf block and sub-tree (pk_rs_encode_sharded + pk_merkle_build) as a commitment, so that pk_commit_open* runs on
+// it with LOCAL row indexes; non-owning.
+int pk_commit_wrap(pk_ctx* ctx, const pk_buf* leaves, const pk_buf* nodes, size_t num_leaves, size_t leaf_width, pk_commitment** out) {
     PK_BIND(ctx);
-    PK_CHECK(ctx, ctx && c && (n_idx == 0 || (sorted_idx && leaves_out && sibling_out && prefix_len_out && suffix_out && suffix_len_out)),
-             "commit_open: null argument");
+    PK_CHECK(ctx, ctx && leaves && nodes && out, "commit_wrap: null argument");
+    PK_CHECK(ctx, num_leaves >= 1 && (num_leaves & (num_leaves - 1)) == 0 && leaf_width >= 1, "commit_wrap: leaf count must be a power of two");
+    PK_CHECK(ctx, leaves->n >= num_leaves * leaf_width && nodes->n >= 2 * num_leaves, "commit_wrap: buffers too small");
+    pk_commitment* c = new pk_commitment();
+    c->leaves = leaves->d;
+    c->nodes = nodes->d;
+    c->L = num_leaves;
+    c->w = leaf_width;
+    c->depth = 0;
+    while (((size_t)1 << c->depth) < num_leaves) c->depth++;
+    c->owns = false;
+    *out = c;
+    return PK_OK;
+}
+// STIR answers and the UNCOMPRESSED authentication paths: paths_out[q][level], level 0 = the sibling leaf digest, level
+// depth-1 = the sibling below the root (canonical digests).  The building block of pk_commit_open; a sharded opening gathers
+// these per owner rank, appends the levels above the sub-trees and compresses once (pk_multipath_build).
+int pk_commit_open_paths(pk_ctx* ctx, const pk_commitment* c, const uint64_t* sorted_idx, size_t n_idx, uint64_t* leaves_out,
+                         uint64_t* paths_out) {
+    PK_BIND(ctx);
+    PK_CHECK(ctx, ctx && c && (n_idx == 0 || (sorted_idx && leaves_out && (paths_out || c->depth == 0))), "commit_open: null argument");
     if (n_idx == 0) return PK_OK;
     for (size_t i = 0; i < n_idx; i++) {
         PK_CHECK(ctx, sorted_idx[i] < c->L, "commit_open: index %llu out of range", (unsigned long long)sorted_idx[i]);
@@ -635,14 +658,21 @@ int pk_commit_open(pk_ctx* ctx, const pk_commitment* c, const uint64_t* sorted_i
     char* d_path = d_rows + n_rows * 32;
     ctx->launches += launch_gather_rows(ctx->stream, c->leaves, c->w, (const uint64_t*)ctx->d_small, n_idx, d_rows);
     if (c->canonical_leaves) ctx->launches += launch_to_mont(ctx->stream, d_rows, n_rows, true);  // the ABI returns field elements
-    ctx->launches += launch_gather_paths(ctx->stream, c->nodes, c->L, (const uint64_t*)ctx->d_small, n_idx, depth, d_path);
+    if (depth > 0) ctx->launches += launch_gather_paths(ctx->stream, c->nodes, c->L, (const uint64_t*)ctx->d_small, n_idx, depth, d_path);
     PK_CUDA(ctx, cudaGetLastError());
     PK_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage, d_rows, (n_rows + n_path) * 32, cudaMemcpyDeviceToHost, ctx->stream));
     PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     std::memcpy(leaves_out, ctx->h_stage, n_rows * 32);
-    const uint64_t* paths = (const uint64_t*)((char*)ctx->h_stage + n_rows * 32);
-    // ark MultiPath: sibling leaf digest + auth path root->leaf (excluding the leaf level), prefix-compressed
-    // against the previous path (recursive-verifier/app/circuit/mt.go:36-50, utilities.go:71-82)
+    if (n_path) std::memcpy(paths_out, (char*)ctx->h_stage + n_rows * 32, n_path * 32);
+    return PK_OK;
+}
+// ark MultiPath from uncompressed paths (paths[q][level], level 0 = sibling leaf digest): sibling leaf digest + auth path
+// root->leaf (excluding the leaf level), prefix-compressed against the previous path
+// (recursive-verifier/app/circuit/mt.go:36-50, utilities.go:71-82).  Host-side bookkeeping, no device work.
+int pk_multipath_build(pk_ctx* ctx, const uint64_t* paths, size_t n_idx, int depth, uint64_t* sibling_out, uint64_t* prefix_len_out,
+                       uint64_t* suffix_out, uint64_t* suffix_len_out, size_t suffix_cap) {
+    PK_CHECK(ctx, depth >= 1 && depth < 64, "multipath_build: a tree with a single leaf has no path");
+    PK_CHECK(ctx, n_idx == 0 || (paths && sibling_out && prefix_len_out && suffix_out && suffix_len_out), "multipath_build: null argument");
     size_t used = 0;
     const int plen = depth - 1;
     for (size_t q = 0; q < n_idx; q++) {
@@ -656,10 +686,21 @@ int pk_commit_open(pk_ctx* ctx, const pk_commitment* c, const uint64_t* sorted_i
         }
         prefix_len_out[q] = (uint64_t)k;
         suffix_len_out[q] = (uint64_t)(plen - k);
-        PK_CHECK(ctx, used + (size_t)(plen - k) <= suffix_cap, "commit_open: suffix_out too small");
+        PK_CHECK(ctx, used + (size_t)(plen - k) <= suffix_cap, "multipath_build: suffix_out too small");
         for (int j = k; j < plen; j++) std::memcpy(suffix_out + 4 * (used++), cur + (size_t)(depth - 1 - j) * 4, 32);
     }
     return PK_OK;
+}
+int pk_commit_open(pk_ctx* ctx, const pk_commitment* c, const uint64_t* sorted_idx, size_t n_idx, uint64_t* leaves_out,
+                   uint64_t* sibling_out, uint64_t* prefix_len_out, uint64_t* suffix_out, uint64_t* suffix_len_out,
+                   size_t suffix_cap) {
+    PK_BIND(ctx);
+    PK_CHECK(ctx, ctx && c && (n_idx == 0 || (sorted_idx && leaves_out && sibling_out && prefix_len_out && suffix_out && suffix_len_out)),
+             "commit_open: null argument");
+    if (n_idx == 0) return PK_OK;
+    std::vector<uint64_t> paths(n_idx * (size_t)c->depth * 4);
+    PK_TRY(pk_commit_open_paths(ctx, c, sorted_idx, n_idx, leaves_out, paths.data()));
+    return pk_multipath_build(ctx, paths.data(), n_idx, c->depth, sibling_out, prefix_len_out, suffix_out, suffix_len_out, suffix_cap);
 }
 
 // ---- univariate / multilinear helpers ------------------------------------------------------------

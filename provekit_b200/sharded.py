@@ -259,6 +259,7 @@ class ShardedCommit:
         sub = self.nodes.download(1, 1)  # canonical sub-tree root
         t.append(time.perf_counter())
         if self.world == 1:
+            self.sub_roots = np.array(sub, copy=True).reshape(1, 4)
             root = ctx.merkle_combine_roots(sub)
         else:
             import torch
@@ -267,12 +268,53 @@ class ShardedCommit:
                 mine = mine.to(self.coll_device)
             out = torch.empty(self.world * 4, dtype=torch.int64, device=mine.device)
             self.dist.all_gather_into_tensor(out, mine)
-            root = ctx.merkle_combine_roots(out.cpu().numpy().view(np.uint64).reshape(self.world, 4))
+            self.sub_roots = out.cpu().numpy().view(np.uint64).reshape(self.world, 4).copy()
+            root = ctx.merkle_combine_roots(self.sub_roots)
         t.append(time.perf_counter())
         # host-clock phases of the last commit on this rank: encode + peer stores, barrier, sub-tree, roots
         self.phases_ms = {k: round((t[i + 1] - t[i]) * 1e3, 3) for i, k in
                           enumerate(("encode_and_exchange", "barrier", "merkle_subtree", "allgather_and_top"))}
         return root
+
+    def open(self, sorted_indexes):
+        """STIR answers + ark MultiPath of the SHARDED commitment for strictly increasing GLOBAL leaf indexes — what
+        Commitment.open returns for the same tree on one GPU (the opening routes each queried index to its owner
+        rank).  Every rank opens its own rows (pk_commit_open_paths on its leaf block and sub-tree), the rows and the
+        uncompressed sub-tree paths are all-gathered in rank order (= index order: ranks own contiguous row ranges), the
+        log2(world) levels above the sub-trees come from the sub-roots of the last commit(), and the paths are
+        prefix-compressed once (pk_multipath_build).  Call after commit(); identical result on every rank."""
+        ctx = self.ctx
+        idx = np.ascontiguousarray(sorted_indexes, dtype=np.uint64)
+        if len(idx) and (np.any(idx[1:] <= idx[:-1]) or int(idx[-1]) >= self.rows):
+            raise ValueError("indexes must be strictly increasing and below the leaf count")
+        owner = (idx // np.uint64(self.per)).astype(np.int64)
+        mine = idx[owner == self.rank] - np.uint64(self.rank * self.per)
+        view = ctx.commit_wrap(self.leaves, self.nodes, self.per, self.w)
+        try:
+            rows, paths = view.open_paths(mine) if len(mine) else (np.empty((0, self.w, 4), np.uint64),
+                                                                     np.empty((0, view.depth, 4), np.uint64))
+            sub_depth = view.depth
+        finally:
+            view.free()
+        if self.world == 1:
+            all_rows, all_paths = rows, paths
+        else:
+            parts = [None] * self.world
+            self.dist.all_gather_object(parts, (rows, paths))
+            all_rows = np.concatenate([p[0] for p in parts], axis=0)
+            all_paths = np.concatenate([p[1] for p in parts], axis=0)
+        # levels above the sub-trees: T[0] = sub-roots, T[j+1][k] = compress(T[j][2k], T[j][2k+1]) (canonical digests)
+        levels = [np.ascontiguousarray(self.sub_roots, dtype=np.uint64).reshape(self.world, 4)]
+        while len(levels[-1]) > 1:
+            cur = levels[-1]
+            levels.append(np.frombuffer(ctx.compress_many(np.ascontiguousarray(cur).tobytes()), dtype=np.uint64).reshape(-1, 4).copy())
+        top = np.empty((len(idx), len(levels) - 1, 4), np.uint64)
+        for q, g in enumerate(owner):
+            for j in range(len(levels) - 1):
+                top[q, j] = levels[j][(int(g) >> j) ^ 1]
+        full = np.concatenate([all_paths.reshape(len(idx), sub_depth, 4), top], axis=1)
+        sib, pre, sufs = ctx.multipath_build(full)
+        return all_rows, sib, pre, sufs
 
     def close(self):
         for p in self.opened:

@@ -191,6 +191,59 @@ def test_commit_batch_and_open(ctx, orc, log_n, rate, batch):
         b.free()
 
 
+@pytest.mark.parametrize("log_n,shards", [(8, 1), (12, 2), (12, 8), (16, 4)])
+def test_sharded_opening_on_one_device(ctx, log_n, shards):
+    """The building blocks of the sharded opening against pk_commit_open on the whole tree: every "rank" opens its
+    rows on a view of its leaf block and sub-tree (pk_commit_wrap + pk_commit_open_paths, local indexes), the levels above
+    the sub-trees are hashed from the sub-roots, pk_multipath_build compresses once.  Ranks are slices of one device here; the
+    multi-process form over CUDA IPC is tests/test_gpu_sharded.py."""
+    polys = [ctx.upload(rng_fr(31 * log_n + b, 1 << log_n)) for b in range(2)]
+    cm = ctx.commit_batch(polys, log_n, 1)
+    L, w = cm.num_leaves, cm.leaf_width
+    per = L // shards
+    rng = np.random.default_rng(shards)
+    idx = np.array(sorted(set(int(i) for i in rng.integers(0, L, size=60)) | {0, 1, L // 2, L - 1}), dtype=np.uint64)
+    exp = cm.open(idx)
+    # one-shot: uncompressed paths of the whole tree -> the same MultiPath
+    rows, paths = cm.open_paths(idx)
+    assert np.array_equal(rows, exp[0])
+    sib, pre, sufs = ctx.multipath_build(paths)
+    assert np.array_equal(sib, exp[1]) and np.array_equal(pre, exp[2]) and all(np.array_equal(a, b) for a, b in zip(sufs, exp[3]))
+    # sharded: rebuild every rank's leaf block and sub-tree, open per rank, combine
+    leaves = np.zeros((L * w, 4), np.uint64).reshape(L, w, 4)
+    for b, poly in enumerate(polys):
+        blk = ctx.buffer(L * 16)
+        ctx.rs_encode(poly, log_n, 1, blk, 16, 0)
+        leaves[:, 16 * b:16 * b + 16] = blk.download().reshape(L, 16, 4)
+        blk.free()
+    sub_roots, all_rows, all_paths, owners = [], [], [], []
+    for g in range(shards):
+        lb, nb = ctx.upload(leaves[g * per:(g + 1) * per].reshape(-1, 4)), ctx.buffer(2 * per)
+        ctx.merkle_build(lb, per, w, nb)
+        sub_roots.append(nb.download(1, 1)[0])
+        view = ctx.commit_wrap(lb, nb, per, w)
+        mine = idx[(idx // np.uint64(per)) == g] - np.uint64(g * per)
+        if len(mine):
+            r_, p_ = view.open_paths(mine)
+            all_rows.append(r_)
+            all_paths.append(p_)
+            owners += [g] * len(mine)
+        view.free()
+        lb.free()
+        nb.free()
+    levels = [np.array(sub_roots, dtype=np.uint64)]
+    while len(levels[-1]) > 1:
+        levels.append(np.frombuffer(ctx.compress_many(np.ascontiguousarray(levels[-1]).tobytes()), dtype=np.uint64).reshape(-1, 4).copy())
+    top = np.array([[levels[j][(g >> j) ^ 1] for j in range(len(levels) - 1)] for g in owners], dtype=np.uint64).reshape(len(idx), -1, 4)
+    full = np.concatenate([np.concatenate(all_paths, axis=0), top], axis=1)
+    sib, pre, sufs = ctx.multipath_build(full)
+    assert np.array_equal(np.concatenate(all_rows, axis=0), exp[0])
+    assert np.array_equal(sib, exp[1]) and np.array_equal(pre, exp[2]) and all(np.array_equal(a, b) for a, b in zip(sufs, exp[3]))
+    cm.free()
+    for b in polys:
+        b.free()
+
+
 def test_commit_open_rejects_unsorted(ctx):
     from provekit_b200 import PkError
     b = ctx.upload(rng_fr(1, 256))

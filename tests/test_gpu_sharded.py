@@ -122,6 +122,7 @@ def test_sharded_commit_multi_process_same_device(world, log_n):
     blocks, gloo carries the barrier and the 32-byte sub-roots.  The root must equal the single-process pk_commit_batch."""
     r = _run_torchrun("sharded_commit.py", world, ["--log-n", str(log_n), "--same-device", "--check", "--steps", "1", "--warmup", "1"])
     assert r["root_matches_single_gpu"] is True and r["n_gpus"] == world and r["same_device"] is True
+    assert r["opening_matches_single_gpu"] is True  # sharded pk_commit_open: rows + ark MultiPath equal the single-GPU opening
 
 
 def _gpu_count():
@@ -138,6 +139,6 @@ def test_sharded_commit_and_sumchecks_over_nvlink(world):
     if _gpu_count() < world:
         pytest.skip(f"needs {world} GPUs")
     r = _run_torchrun("sharded_commit.py", world, ["--log-n", "18", "--check", "--steps", "1", "--warmup", "1"])
-    assert r["root_matches_single_gpu"] is True and r["n_gpus"] == world
+    assert r["root_matches_single_gpu"] is True and r["opening_matches_single_gpu"] is True and r["n_gpus"] == world
     r = _run_torchrun("sharded_sumcheck.py", world, ["--log-n", "16", "--check", "--steps", "1", "--warmup", "1"])
     assert r["messages_match_unsharded"] is True and r["n_gpus"] == world

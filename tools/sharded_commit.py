@@ -71,10 +71,22 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=coll_device if coll_device is not None else "cpu")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    ok = None
+    ok, open_ok, open_ms = None, None, None
+    if args.check:
+        # a STIR-sized opening through the sharded tree (every rank takes part), compared with the single-GPU opening
+        qrng = np.random.default_rng(99)
+        idx = np.unique(qrng.integers(0, rows, size=min(109, rows), dtype=np.uint64))
+        if rows >= 4:
+            idx = np.unique(np.concatenate([idx, np.array([0, 1, rows // 2, rows - 1], dtype=np.uint64)]))
+        t0 = time.perf_counter()
+        got = sc.open(idx)
+        open_ms = (time.perf_counter() - t0) * 1e3
     if args.check and rank == 0:
         cm = ctx.commit_batch(polys, log_n, rate)
         ok = bool(np.array_equal(sharded.to_montgomery(root), cm.root))  # cm.root is Montgomery, ours canonical
+        exp = cm.open(idx)
+        open_ok = bool(np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1]) and np.array_equal(got[2], exp[2])
+                       and len(got[3]) == len(exp[3]) and all(np.array_equal(a, b) for a, b in zip(got[3], exp[3])))
         cm.free()
     if rank == 0:
         nbytes_ntt = batch * 96 * n
@@ -83,7 +95,8 @@ def main():
                           "n_gpus": world, "same_device": args.same_device, "ms_per_commit": ms, "commits_per_s": 1e3 / ms,
                           "alg_gbs_ntt_plus_merkle": (nbytes_ntt + nbytes_mrk) / ms / 1e6,
                           "exchange": "fused into the last NTT pass (peer stores via CUDA IPC) + all_gather of sub-roots over " + backend,
-                          "root_matches_single_gpu": ok, "root": [int(x) for x in root]}))
+                          "root_matches_single_gpu": ok, "opening_matches_single_gpu": open_ok, "open_ms": open_ms,
+                          "root": [int(x) for x in root]}))
     if world > 1:
         dist.barrier()
     sc.close()
