@@ -29,17 +29,17 @@ static_assert(sizeof(DevTs) == 96, "DevTs layout");
 enum { TS_ERR_OVERFLOW = 1, TS_ERR_IDENTITY = 2, TS_ERR_POW = 3 };
 
 // the 18-round Skyscraper-v2 permutation on canonical (l, r) -> canonical (l', r') (reference.rs:49-60); same paired
-// Feistel rounds and lazy reduction as sky_compress
+// Feistel rounds and lazy reduction as sky_compress (register-only round sums: one thread, latency-bound)
 static __device__ __noinline__ void sky_permute(fr& l, fr& r) {
 #pragma unroll 1
     for (int j = 0; j < 9; j++) {
         const bool is_bar = (j == 3) | (j == 5);
         if (is_bar) {
-            r = sky_reduce_2p(add3_raw(r, sky_bar(sky_canon(l)), sky_rc(2 * j)));
-            l = sky_reduce_2p(add3_raw(l, sky_bar(sky_canon(r)), sky_rc(2 * j + 1)));
+            r = sky_round_sum<0>(r, sky_bar(sky_canon(l)), 2 * j);
+            l = sky_round_sum<0>(l, sky_bar(sky_canon(r)), 2 * j + 1);
         } else {
-            r = sky_reduce_2p(add3_raw(r, fr_sqr_lazy(l), sky_rc(2 * j)));
-            l = sky_reduce_2p(add3_raw(l, fr_sqr_lazy(r), sky_rc(2 * j + 1)));
+            r = sky_round_sum<0>(r, fr_sqr_lazy(l), 2 * j);
+            l = sky_round_sum<0>(l, fr_sqr_lazy(r), 2 * j + 1);
         }
     }
     l = sky_canon(l);

@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(1024) k_merkle_reduce(fr* nodes, size_t n_in, 
         lvl >>= 1;
         off >>= 1;
         if (act) {
-            fr h = sky_compress(a, b);
+            fr h = sky_compress<0>(a, b);  // latency-bound tree levels: register-only round sums
             sd[tid] = h;
             fr_store(&nodes[lvl + off + tid], h);
             if (root_mont_out && lvl == 1) fr_store(root_mont_out, fr_to_mont(h));
