@@ -937,6 +937,19 @@ namespace {
 // H2D staging of one proof's inputs: witness (zero-padded) || mask, g, blinding cubics || mask, g.  do_sync: return only
 // when the host arrays may be reused (the stand-alone entry points); inside pk_prove the proof's own final
 // synchronisation covers it
+// H2D in pieces of PK_H2D_CHUNK_MB (0 / unset: one copy): experiment knob, see DESIGN.md section 6
+static cudaError_t h2d(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    static const size_t chunk = [] {
+        const char* e = std::getenv("PK_H2D_CHUNK_MB");
+        return e ? (size_t)std::atoi(e) << 20 : (size_t)0;
+    }();
+    if (!chunk || bytes <= chunk) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+    for (size_t off = 0; off < bytes; off += chunk) {
+        cudaError_t e = cudaMemcpyAsync((char*)dst + off, (const char*)src + off, std::min(chunk, bytes - off), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
 int upload_inputs(pk_prover* p, const uint64_t* witness, const pk_rand* rnd, bool do_sync) {
     if (!p) return PK_ERR_INVALID_ARG;
     pk_ctx* ctx = p->ctx;
@@ -956,9 +969,9 @@ int upload_inputs(pk_prover* p, const uint64_t* witness, const pk_rand* rnd, boo
     cudaStream_t st = ctx->stream;
     // create_masked_polynomial (zk_utils.rs:3-11): [pad_to_power_of_two(witness) || mask]
     PK_CUDA(ctx, cudaMemsetAsync((char*)p->masked_w->d + p->num_witnesses * 32, 0, (half - p->num_witnesses) * 32, st));
-    PK_CUDA(ctx, cudaMemcpyAsync(p->masked_w->d, witness, p->num_witnesses * 32, cudaMemcpyHostToDevice, st));
-    PK_CUDA(ctx, cudaMemcpyAsync((char*)p->masked_w->d + half * 32, rnd->mask_w, half * 32, cudaMemcpyHostToDevice, st));
-    PK_CUDA(ctx, cudaMemcpyAsync(p->g_w->d, rnd->g_w, N * 32, cudaMemcpyHostToDevice, st));
+    PK_CUDA(ctx, h2d(p->masked_w->d, witness, p->num_witnesses * 32, st));
+    PK_CUDA(ctx, h2d((char*)p->masked_w->d + half * 32, rnd->mask_w, half * 32, st));
+    PK_CUDA(ctx, h2d(p->g_w->d, rnd->g_w, N * 32, st));
     PK_CUDA(ctx, cudaMemsetAsync(p->masked_h->d, 0, halfh * 32, st));
     PK_CUDA(ctx, cudaMemcpyAsync(p->masked_h->d, rnd->blind, 4 * (size_t)p->m0 * 32, cudaMemcpyHostToDevice, st));
     PK_CUDA(ctx, cudaMemcpyAsync((char*)p->masked_h->d + halfh * 32, rnd->mask_h, halfh * 32, cudaMemcpyHostToDevice, st));
