@@ -229,8 +229,12 @@ __device__ __forceinline__ void mont_row(uint32_t* e, uint32_t* o, const fr& a, 
     o[7] += mad4(e, PK_P0, PK_P2, PK_P4, PK_P6, m);
 }
 
-// a * b * 2^-256 mod p, inputs in [0, p) (Montgomery form or raw, see skyscraper.cuh), output in [0, p)
-__device__ __forceinline__ fr fr_mul(const fr& a, const fr& b) {
+// a * b * 2^-256 mod p.  LAZY = false: inputs in [0, p) (Montgomery form or raw, see skyscraper.cuh), output in [0, p).
+// LAZY = true: a in [0, 4p], b in [0, p), output (a b + m p) / 2^256 < 4p * 0.19 + p < 2p WITHOUT the final conditional
+// subtraction.  The rows are the same: every row's running sum is below (a + p) * 2^32 < 2^288 because 5p < 2^256, so the
+// ninth limb (o[7] after the role swap) still never overflows.
+template <bool LAZY = false>
+__device__ __forceinline__ fr fr_mul_t(const fr& a, const fr& b) {
     uint32_t e[8], o[8];
     mont_row<true>(e, o, a, b.v[0]);
     mont_row<false>(o, e, a, b.v[1]);
@@ -254,8 +258,90 @@ __device__ __forceinline__ fr fr_mul(const fr& a, const fr& b) {
           "=r"(r.v[7])
         : "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(o[1]),
           "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]));
-    return fr_reduce_once(r);
+    return LAZY ? r : fr_reduce_once(r);
 }
+__device__ __forceinline__ fr fr_mul(const fr& a, const fr& b) { return fr_mul_t<false>(a, b); }
+__device__ __forceinline__ fr fr_mul_lazy(const fr& a, const fr& b) { return fr_mul_t<true>(a, b); }
+// ---- lazily reduced forms for butterfly networks (ntt.cu): values live in [0, 2p] between butterflies ----------------
+// 2p (skyscraper/core/src/constants.rs:9-16 MODULUS[2])
+#define PK_2P0 0xe0000002u
+#define PK_2P1 0x87c3eb27u
+#define PK_2P2 0xf372e122u
+#define PK_2P3 0x5067d090u
+#define PK_2P4 0x0302b0bau
+#define PK_2P5 0x70a08b6du
+#define PK_2P6 0xc2634053u
+#define PK_2P7 0x60c89ce5u
+// a in [0, 4p] -> [0, 2p]: one conditional subtraction of 2p
+__device__ __forceinline__ fr fr_reduce_2p_once(const fr& a) {
+    fr t;
+    uint32_t borrow;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(t.v[0]), "=r"(t.v[1]), "=r"(t.v[2]), "=r"(t.v[3]), "=r"(t.v[4]), "=r"(t.v[5]), "=r"(t.v[6]), "=r"(t.v[7]), "=r"(borrow)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(PK_2P0), "r"(PK_2P1), "r"(PK_2P2), "r"(PK_2P3), "r"(PK_2P4), "r"(PK_2P5), "r"(PK_2P6), "r"(PK_2P7));
+    fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = borrow ? a.v[i] : t.v[i];
+    return r;
+}
+// a, b in [0, 2p] -> a + b in [0, 2p] (a + b <= 4p < 2^256)
+__device__ __forceinline__ fr fr_add_lazy(const fr& a, const fr& b) {
+    fr s;
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=r"(s.v[0]), "=r"(s.v[1]), "=r"(s.v[2]), "=r"(s.v[3]), "=r"(s.v[4]), "=r"(s.v[5]), "=r"(s.v[6]), "=r"(s.v[7])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    return fr_reduce_2p_once(s);
+}
+// a, b in [0, 2p] -> a - b + 2p in [0, 4p]: NOT reduced (the twiddle product that follows accepts it)
+__device__ __forceinline__ fr fr_sub_lazy(const fr& a, const fr& b) {
+    fr d;
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=r"(d.v[0]), "=r"(d.v[1]), "=r"(d.v[2]), "=r"(d.v[3]), "=r"(d.v[4]), "=r"(d.v[5]), "=r"(d.v[6]), "=r"(d.v[7])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(PK_2P0), "r"(PK_2P1), "r"(PK_2P2), "r"(PK_2P3), "r"(PK_2P4), "r"(PK_2P5), "r"(PK_2P6), "r"(PK_2P7));
+    asm("sub.cc.u32 %0, %0, %8;\n\t"
+        "subc.cc.u32 %1, %1, %9;\n\t"
+        "subc.cc.u32 %2, %2, %10;\n\t"
+        "subc.cc.u32 %3, %3, %11;\n\t"
+        "subc.cc.u32 %4, %4, %12;\n\t"
+        "subc.cc.u32 %5, %5, %13;\n\t"
+        "subc.cc.u32 %6, %6, %14;\n\t"
+        "subc.u32 %7, %7, %15;"
+        : "+r"(d.v[0]), "+r"(d.v[1]), "+r"(d.v[2]), "+r"(d.v[3]), "+r"(d.v[4]), "+r"(d.v[5]), "+r"(d.v[6]), "+r"(d.v[7])
+        : "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    return d;
+}
+// [0, 2p] -> 2p - a in [0, 2p]
+__device__ __forceinline__ fr fr_neg_lazy(const fr& a) {
+    fr z = fr_zero();
+    return fr_reduce_2p_once(fr_sub_lazy(z, a));  // 2p - a <= 2p: the reduction only maps 2p -> 0
+}
+// [0, 2p] -> canonical representative in [0, p)
+__device__ __forceinline__ fr fr_normalize_2p(const fr& a) { return fr_reduce_once(fr_reduce_once(a)); }
 #include "fr_sqr.inc"
 
 // canonical integer < p  ->  Montgomery form

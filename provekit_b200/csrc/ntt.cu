@@ -88,10 +88,29 @@ static __device__ __forceinline__ void tile_put(uint4* tile, int e, int swap, co
     p[swap ^ 1] = swap ? a : b;
 }
 
-// one radix-2^G step over stage bits [hb0, hb0 + G) of the tile (DIF: highest bit first)
+// Lazy reduction (PK_NTT_LAZY, default on): tile values live in [0, 2p] between butterflies and passes.  a + b is reduced by
+// one conditional subtraction of 2p, a - b + 2p in [0, 4p] goes unreduced into the twiddle product, whose Montgomery rows
+// accept it and return a value below 2p without the final conditional subtraction (fr.cuh); only the last step of the
+// last pass normalises to [0, p).  26 fewer ALU-pipe instructions per butterfly; the codeword is bit-identical.
+#ifndef PK_NTT_LAZY
+#define PK_NTT_LAZY 1
+#endif
+#if PK_NTT_LAZY
+#define NTT_ADD fr_add_lazy
+#define NTT_SUB fr_sub_lazy
+#define NTT_MUL fr_mul_lazy
+#define NTT_NEG fr_neg_lazy
+#else
+#define NTT_ADD fr_add
+#define NTT_SUB fr_sub
+#define NTT_MUL fr_mul
+#define NTT_NEG fr_neg
+#endif
+// one radix-2^G step over stage bits [hb0, hb0 + G) of the tile (DIF: highest bit first); `final`: the last step of the last
+// pass (values leave for the leaves: canonical representatives)
 template <int G>
 static __device__ __forceinline__ void ntt_step(uint4* tile, const fr* tw, const NttR8& P, int hb0, uint32_t Lo, bool twist,
-                                                uint32_t s, uint32_t qbase) {
+                                                uint32_t s, uint32_t qbase, bool final) {
     constexpr int R = 1 << G;
     const int items = (1 << (P.S - G)) << NTT8_NCL;
     for (int item = threadIdx.x; item < items; item += blockDim.x) {
@@ -113,10 +132,10 @@ static __device__ __forceinline__ void ntt_step(uint4* tile, const fr* tw, const
                 const bool neg = e >= halfM;
                 e &= halfM - 1u;
                 if (e)
-                    x[c] = fr_mul(x[c], fr_load_nc(&P.Wtwist[(size_t)e << P.tbl_shift]));
+                    x[c] = NTT_MUL(x[c], fr_load_nc(&P.Wtwist[(size_t)e << P.tbl_shift]));
                 else if (P.canonical)
                     x[c] = fr_from_mont(x[c]);
-                if (neg) x[c] = fr_neg(x[c]);
+                if (neg) x[c] = NTT_NEG(x[c]);
             }
         }
 #pragma unroll
@@ -128,12 +147,23 @@ static __device__ __forceinline__ void ntt_step(uint4* tile, const fr* tw, const
                 const int c1 = c | (1 << sbit);
                 const int j = low | ((c & ((1 << sbit) - 1)) << hb0);  // position inside the half-size-2^hb butterfly group
                 const fr a = x[c], b = x[c1];
-                x[c] = fr_add(a, b);
-                fr d = fr_sub(a, b);
-                if ((uint32_t)j | Lo) d = fr_mul(d, fr_load(&tw[(1 << hb) - 1 + j]));  // (j, Lo) = (0, 0): twiddle 1
+                x[c] = NTT_ADD(a, b);
+                fr d = NTT_SUB(a, b);
+                if ((uint32_t)j | Lo)
+                    d = NTT_MUL(d, fr_load(&tw[(1 << hb) - 1 + j]));
+#if PK_NTT_LAZY
+                else
+                    d = fr_reduce_2p_once(d);  // (j, Lo) = (0, 0): twiddle 1, only the range has to come back to [0, 2p]
+#endif
                 x[c1] = d;
             }
         }
+#if PK_NTT_LAZY
+        if (final) {
+#pragma unroll
+            for (int c = 0; c < R; c++) x[c] = fr_normalize_2p(x[c]);
+        }
+#endif
 #pragma unroll
         for (int c = 0; c < R; c++) tile_put(tile, ((e0 + (c << hb0)) << NTT8_NCL) + k, swap, x[c]);
     }
@@ -183,12 +213,13 @@ __global__ void __launch_bounds__(256, 2) k_ntt_r8(NttR8 P) {
     bool twist = P.first != 0 && (s != 0 || P.canonical);
     for (int hb = S; hb > 0;) {  // stage bits [hb - g, hb)
         const int g = hb >= 3 ? 3 : hb;
+        const bool final = P.last != 0 && hb == g;
         if (g == 3)
-            ntt_step<3>(tile, tw, P, hb - 3, Lo, twist, s, qbase);
+            ntt_step<3>(tile, tw, P, hb - 3, Lo, twist, s, qbase, final);
         else if (g == 2)
-            ntt_step<2>(tile, tw, P, hb - 2, Lo, twist, s, qbase);
+            ntt_step<2>(tile, tw, P, hb - 2, Lo, twist, s, qbase, final);
         else
-            ntt_step<1>(tile, tw, P, hb - 1, Lo, twist, s, qbase);
+            ntt_step<1>(tile, tw, P, hb - 1, Lo, twist, s, qbase, final);
         twist = false;
         hb -= g;
         if (hb > 0) __syncthreads();
