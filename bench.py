@@ -39,7 +39,7 @@ from tools import workload as wl  # noqa: E402
 
 REPEATS = 5          # timed repetitions; the MEDIAN is reported (config.timing)
 MIN_REGION_STEPS = 150   # a timed repetition covers ceil(MIN_REGION_STEPS / K) * K proofs (>= 1 s), whatever --steps is
-IN_FLIGHT = 16       # independent proofs in flight per GPU, fixed (not derived from --steps)
+IN_FLIGHT = 24       # independent proofs in flight per GPU, fixed (not derived from --steps)
 
 WORKLOADS = {
     # configs[1]: poseidon-rounds shapes (fixture poseidon-1000.nps): m = 21, m_0 = 20
