@@ -201,6 +201,14 @@ int pk_whir_sumcheck_round(pk_ctx *ctx, const pk_buf *p_in, const pk_buf *w_in, 
 size_t pk_shard_mailbox_elems(void);
 int pk_shard_group_set(pk_ctx *ctx, int rank, int world, void *const *mailboxes);
 int pk_shard_group_clear(pk_ctx *ctx);
+/* The same mailboxes carry the two collectives of the SHARDED COMMITMENT, so that it needs no host collective at all:
+ *   pk_shard_barrier   : barrier on the stream (asynchronous): kernels enqueued behind it start once every rank has reached
+ *                        its own barrier — between pk_rs_encode_sharded (peer stores into the other ranks' rows) and
+ *                        pk_merkle_build of the local rows.
+ *   pk_shard_allgather : out[r] = rank r's src[off] (one field element = one sub-tree root per rank, rank order); synchronises.
+ * Every rank must issue the same sequence of sharded calls (rounds, barriers, all-gathers). */
+int pk_shard_barrier(pk_ctx *ctx);
+int pk_shard_allgather(pk_ctx *ctx, const pk_buf *src, size_t off, uint64_t *out);
 int pk_zk_sumcheck_round_sharded(pk_ctx *ctx, pk_buf *a, pk_buf *b, pk_buf *c, pk_buf *eq, int log_n,
                                  const uint64_t *fold_or_null, uint64_t out3[12]);
 int pk_whir_sumcheck_round_sharded(pk_ctx *ctx, const pk_buf *p_in, const pk_buf *w_in, pk_buf *p_out, pk_buf *w_out,

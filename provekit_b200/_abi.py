@@ -104,6 +104,8 @@ def lib() -> ctypes.CDLL:
         "pk_shard_mailbox_elems": (sz, []),
         "pk_shard_group_set": (c_int, [vp, c_int, c_int, POINTER(vp)]),
         "pk_shard_group_clear": (c_int, [vp]),
+        "pk_shard_barrier": (c_int, [vp]),
+        "pk_shard_allgather": (c_int, [vp, vp, sz, u64p]),
         "pk_zk_sumcheck_round_sharded": (c_int, [vp, vp, vp, vp, vp, c_int, u64p, u64p]),
         "pk_whir_sumcheck_round_sharded": (c_int, [vp, vp, vp, vp, vp, c_int, u64p, u64p]),
         "pk_prover_create": (c_int, [vp, POINTER(R1CS), POINTER(vp)]),

@@ -333,6 +333,16 @@ class Context:
         arr = (c_void_p * world)(*[c_void_p(int(p)) for p in mailbox_ptrs])
         self._chk(self.L.pk_shard_group_set(self.h, rank, world, arr))
 
+    def shard_barrier(self):
+        """barrier on the stream across the shard group (asynchronous, pk_shard_barrier)"""
+        self._chk(self.L.pk_shard_barrier(self.h))
+
+    def shard_allgather(self, src: Buffer, off: int, world: int) -> np.ndarray:
+        """(world, 4): rank r's src[off], gathered over the peer mailboxes (pk_shard_allgather; synchronises)"""
+        out = np.empty((world, 4), np.uint64)
+        self._chk(self.L.pk_shard_allgather(self.h, src.h, off, _p(out)))
+        return out
+
     def sumcheck_fold_map_reduce_sharded(self, a: Buffer, b: Buffer, c: Buffer, eq: Buffer, log_n: int, fold=None) -> np.ndarray:
         """the round on the local low-bit shard + exchange over peer memory: the GLOBAL [f(0), f(-1), f(inf)]"""
         out = np.empty((3, 4), np.uint64)

@@ -897,7 +897,13 @@ static __device__ __forceinline__ fr ld_sys(const void* p) {
     for (int i = 0; i < 8; i++) r.v[i] = q[i];
     return r;
 }
-__global__ void __launch_bounds__(32) k_shard_exchange(fr* result, ShardGroup G, uint32_t seq, uint32_t* status) {
+// GATHER = false: result[0..3) <- field sum over the ranks of their result[0..3) (the sumcheck round message).
+// GATHER = true : gathered[3 r .. 3 r + 3) <- rank r's result[0..3), nothing summed: an all-gather of 96 bytes per rank, and —
+// whatever the payload — a barrier ON THE STREAM: kernels enqueued behind it start only after every rank of the group has
+// reached the same point of ITS stream (the sharded commitment: a rank's rows are complete once every peer's last NTT pass,
+// which stores into them over NVLink, is done).
+template <bool GATHER>
+__global__ void __launch_bounds__(32) k_shard_exchange(fr* result, ShardGroup G, uint32_t seq, uint32_t* status, fr* gathered) {
     const int lane = threadIdx.x;
     const size_t slot = seq % SHARD_SLOTS;
     bool ok = true;
@@ -926,16 +932,27 @@ __global__ void __launch_bounds__(32) k_shard_exchange(fr* result, ShardGroup G,
             for (int s = 0; s < 3; s++) v[s] = ld_sys(src + 32 * s);
     }
     ok = __all_sync(0xffffffffu, ok);
+    if (GATHER) {
+        if (lane < G.world)
 #pragma unroll
-    for (int s = 0; s < 3; s++) {
+            for (int s = 0; s < 3; s++) fr_store(&gathered[3 * lane + s], v[s]);
+    } else {
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) v[s] = fr_add(v[s], fr_shfl_down(v[s], d));
-        if (lane == 0) fr_store(&result[s], v[s]);
+        for (int s = 0; s < 3; s++) {
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) v[s] = fr_add(v[s], fr_shfl_down(v[s], d));
+            if (lane == 0) fr_store(&result[s], v[s]);
+        }
     }
-    if (lane == 0) *status = ok ? 0u : 1u;
+    // sticky: a time-out on an earlier exchange of this stream must not be overwritten by a later success
+    if (lane == 0 && !ok) *status = 1u;
 }
 int launch_shard_exchange(cudaStream_t st, void* result, ShardGroup g, uint32_t seq, uint32_t* status) {
-    k_shard_exchange<<<1, 32, 0, st>>>((fr*)result, g, seq, status);
+    k_shard_exchange<false><<<1, 32, 0, st>>>((fr*)result, g, seq, status, nullptr);
+    return 1;
+}
+int launch_shard_gather(cudaStream_t st, void* payload3, ShardGroup g, uint32_t seq, uint32_t* status, void* gathered) {
+    k_shard_exchange<true><<<1, 32, 0, st>>>((fr*)payload3, g, seq, status, (fr*)gathered);
     return 1;
 }
 

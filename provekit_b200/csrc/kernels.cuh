@@ -129,6 +129,8 @@ struct ShardGroup {
     int rank, world;
 };
 int launch_shard_exchange(cudaStream_t st, void* result, ShardGroup g, uint32_t seq, uint32_t* status);
+// all-gather of 3 elements per rank into gathered[3 * world] + stream barrier across the group (see k_shard_exchange)
+int launch_shard_gather(cudaStream_t st, void* payload3, ShardGroup g, uint32_t seq, uint32_t* status, void* gathered);
 
 // interned-CSR sparse matrix x vector (provekit/common/src/sparse_matrix.rs:148-184): out[r] = sum_k
 // interned[val[k]] * x[col[k]] over row r.  The transposed product uses the same kernel on the CSC arrays.

@@ -49,6 +49,7 @@ struct pk_ctx {
     pk::ShardGroup shard = {};
     uint32_t shard_seq = 0;
     uint32_t* d_shard_status = nullptr;
+    void* d_shard_gather = nullptr;  // 3 * SHARD_MAX_WORLD elements: the all-gathered payloads of pk_shard_barrier / pk_shard_allgather
     // optional per-kernel-class CUDA-event timing (pk_profile_begin/end)
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;

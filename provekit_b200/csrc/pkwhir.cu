@@ -171,6 +171,7 @@ void pk_ctx_destroy(pk_ctx* ctx) {
     cudaFree(ctx->d_partials);
     cudaFree(ctx->d_result);
     if (ctx->d_shard_status) cudaFree(ctx->d_shard_status);
+    if (ctx->d_shard_gather) cudaFree(ctx->d_shard_gather);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     cudaFree(ctx->d_best);
     cudaFree(ctx->d_twiddles);
@@ -996,6 +997,8 @@ int pk_shard_group_set(pk_ctx* ctx, int rank, int world, void* const* mailboxes)
              "shard_group_set: world must be a power of two <= %d and 0 <= rank < world", SHARD_MAX_WORLD);
     for (int i = 0; i < world; i++) PK_CHECK(ctx, mailboxes[i] != nullptr, "shard_group_set: mailbox %d is null", i);
     if (!ctx->d_shard_status) PK_CUDA(ctx, cudaMalloc((void**)&ctx->d_shard_status, 4));
+    if (!ctx->d_shard_gather) PK_CUDA(ctx, cudaMalloc(&ctx->d_shard_gather, (size_t)3 * SHARD_MAX_WORLD * 32));
+    PK_CUDA(ctx, cudaMemsetAsync(ctx->d_shard_status, 0, 4, ctx->stream));  // sticky failure flag of the exchange kernels
     ctx->shard = {};
     for (int i = 0; i < world; i++) ctx->shard.mbox[i] = (uint8_t*)mailboxes[i];
     ctx->shard.rank = rank;
@@ -1034,6 +1037,41 @@ static int exchange_and_fetch(pk_ctx* ctx, uint64_t out3[12]) {
         ctx->shard_seq = 0;
         return set_err(ctx, PK_ERR_CUDA, "sharded round %u: a peer did not publish its partial sums in time; group disabled", seq);
     }
+    return PK_OK;
+}
+// Barrier ON THE STREAM across the group (no host synchronisation): what is enqueued behind it starts only after every rank
+// has reached its own pk_shard_barrier.  The sharded commitment puts it between the last NTT pass (which stores rows into the
+// peers' leaf blocks) and the leaf hashing.  A rank that never arrives makes the NEXT synchronising call of the group fail.
+int pk_shard_barrier(pk_ctx* ctx) {
+    PK_BIND(ctx);
+    PK_CHECK(ctx, ctx && ctx->shard.world >= 1, "shard_barrier without pk_shard_group_set");
+    ctx->launches += launch_shard_gather(ctx->stream, ctx->d_result, ctx->shard, ++ctx->shard_seq, ctx->d_shard_status, ctx->d_shard_gather);
+    PK_CUDA(ctx, cudaGetLastError());
+    return PK_OK;
+}
+// All-gather of ONE field element per rank over the peer mailboxes: out[r] = rank r's src[off] (4 limbs each, rank order),
+// identical on every rank.  The sharded commitment gathers the sub-tree roots with it (32 bytes per rank) instead of a host
+// collective.  Synchronises the stream; also a barrier like pk_shard_barrier.
+int pk_shard_allgather(pk_ctx* ctx, const pk_buf* src, size_t off, uint64_t* out) {
+    PK_BIND(ctx);
+    PK_CHECK(ctx, ctx && src && out && off < src->n, "shard_allgather: bad argument");
+    PK_CHECK(ctx, ctx->shard.world >= 1, "shard_allgather without pk_shard_group_set");
+    const int world = ctx->shard.world;
+    PK_CUDA(ctx, cudaMemcpyAsync(ctx->d_result, (const char*)src->d + off * 32, 32, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->launches += launch_shard_gather(ctx->stream, ctx->d_result, ctx->shard, ++ctx->shard_seq, ctx->d_shard_status, ctx->d_shard_gather);
+    PK_CUDA(ctx, cudaGetLastError());
+    PK_CUDA(ctx, cudaMemcpyAsync(ctx->h_result, ctx->d_shard_gather, (size_t)3 * world * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(ctx, cudaMemcpyAsync(ctx->h_result + 12 * SHARD_MAX_WORLD, ctx->d_shard_status, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    uint32_t status = 0;
+    std::memcpy(&status, ctx->h_result + 12 * SHARD_MAX_WORLD, 4);
+    if (status != 0) {
+        uint32_t seq = ctx->shard_seq;
+        ctx->shard = {};
+        ctx->shard_seq = 0;
+        return set_err(ctx, PK_ERR_CUDA, "shard_allgather (exchange %u): a peer did not arrive in time; group disabled", seq);
+    }
+    for (int r = 0; r < world; r++) std::memcpy(out + 4 * r, ctx->h_result + 12 * r, 32);
     return PK_OK;
 }
 int pk_zk_sumcheck_round_sharded(pk_ctx* ctx, pk_buf* a, pk_buf* b, pk_buf* c, pk_buf* eq, int log_n, const uint64_t* fold,

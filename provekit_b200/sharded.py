@@ -229,17 +229,25 @@ class ShardedCommit:
         self.nodes = ctx.buffer(2 * self.per)
         self.coll_device = coll_device
         self.opened = []
+        self.mbox = None
         if world > 1:
+            # leaf blocks AND mailboxes of all ranks mapped over CUDA IPC: the codeword exchange is peer stores from the last
+            # NTT pass, the two collectives of a commit (rows complete; sub-roots) are one-warp kernels over the mailboxes
+            self.mbox = ctx.shard_mailbox()
             handles = [None] * world
-            dist.all_gather_object(handles, ctx.ipc_export(self.leaves))
-            self.peers = []
+            dist.all_gather_object(handles, (ctx.ipc_export(self.leaves), ctx.ipc_export(self.mbox)))
+            self.peers, boxes = [], []
             for r in range(world):
                 if r == rank:
                     self.peers.append(self.leaves.device_ptr)
+                    boxes.append(self.mbox.device_ptr)
                 else:
-                    p = ctx.ipc_open(handles[r])
-                    self.opened.append(p)
-                    self.peers.append(p)
+                    for h, dst in ((handles[r][0], self.peers), (handles[r][1], boxes)):
+                        p = ctx.ipc_open(h)
+                        self.opened.append(p)
+                        dst.append(p)
+            ctx.shard_group(rank, world, boxes)
+            dist.barrier()  # every rank has wiped its mailbox before anyone's first exchange
         else:
             self.peers = [self.leaves.device_ptr]
 
@@ -250,30 +258,25 @@ class ShardedCommit:
         t = [time.perf_counter()]
         for b, cs in self.groups.items():
             ctx.rs_encode_sharded(self.polys[b], self.log_n, self.rate, min(cs), len(cs), self.peers, self.w, 16 * b)
-        ctx.sync()
         t.append(time.perf_counter())
         if self.world > 1:
-            self.dist.barrier()  # a rank's rows are complete only after ALL peers finished storing into them
-        t.append(time.perf_counter())
+            # a rank's rows are complete only after ALL peers finished storing into them: a barrier ON THE STREAM (one-warp
+            # kernel over the peer mailboxes), no host synchronisation and no host collective
+            ctx.shard_barrier()
         ctx.merkle_build(self.leaves, self.per, self.w, self.nodes)
-        sub = self.nodes.download(1, 1)  # canonical sub-tree root
         t.append(time.perf_counter())
         if self.world == 1:
-            self.sub_roots = np.array(sub, copy=True).reshape(1, 4)
-            root = ctx.merkle_combine_roots(sub)
+            self.sub_roots = self.nodes.download(1, 1).reshape(1, 4).copy()  # canonical sub-tree root
         else:
-            import torch
-            mine = torch.from_numpy(sub.view(np.int64).reshape(-1).copy())
-            if self.coll_device is not None:
-                mine = mine.to(self.coll_device)
-            out = torch.empty(self.world * 4, dtype=torch.int64, device=mine.device)
-            self.dist.all_gather_into_tensor(out, mine)
-            self.sub_roots = out.cpu().numpy().view(np.uint64).reshape(self.world, 4).copy()
-            root = ctx.merkle_combine_roots(self.sub_roots)
+            # the sub-roots (32 B per rank) gathered over the same mailboxes; the first host synchronisation of the commit
+            self.sub_roots = ctx.shard_allgather(self.nodes, 1, self.world)
         t.append(time.perf_counter())
-        # host-clock phases of the last commit on this rank: encode + peer stores, barrier, sub-tree, roots
+        root = ctx.merkle_combine_roots(self.sub_roots)
+        t.append(time.perf_counter())
+        # host-clock phases of the last commit on this rank (the first two only enqueue; the device work is waited for in the
+        # third)
         self.phases_ms = {k: round((t[i + 1] - t[i]) * 1e3, 3) for i, k in
-                          enumerate(("encode_and_exchange", "barrier", "merkle_subtree", "allgather_and_top"))}
+                          enumerate(("enqueue_encode", "enqueue_barrier_and_subtree", "wait_and_allgather_subroots", "top_levels"))}
         return root
 
     def open(self, sorted_indexes):
@@ -320,6 +323,10 @@ class ShardedCommit:
         for p in self.opened:
             self.ctx.ipc_close(p)
         self.opened = []
+        if self.mbox is not None:
+            self.ctx.L.pk_shard_group_clear(self.ctx.h)
+            self.mbox.free()
+            self.mbox = None
         self.leaves.free()
         self.nodes.free()
 
@@ -537,6 +544,7 @@ def bench_sharded(pk, ctx, dist, rank: int, world: int, coll_device, log_n_commi
             "sumcheck_messages_match_single_gpu": msgs_ok,
             "commit_phases_ms_rank0": phases, "exchange": "ipc-peer-store", "nvlink": nvlink,
             "exchange_detail": "codeword transpose fused into the last NTT pass as NVLink peer stores into CUDA-IPC mapped leaf blocks; "
-                               "sub-tree roots all-gathered (32 B per rank); sumcheck round messages exchanged by a one-warp kernel over "
-                               "peer mailboxes and summed on the device",
+                               "the 'rows complete' barrier and the all-gather of the sub-tree roots (32 B per rank) are one-warp kernels "
+                               "over peer mailboxes (no host collective in a commit); sumcheck round messages exchanged the same way and "
+                               "summed on the device",
             "timing": f"host clock around stream-synchronised regions, best of {steps} steps for the sumchecks, mean for the commit, max over ranks"}

@@ -1,7 +1,7 @@
 """Sharded WHIR commitment across the GPUs of one box (BASELINE config 4): launched with torchrun, one
 process per GPU.  Columns of the codeword are sharded for the NTT, rows (Merkle leaves) for hashing; the exchange is
-fused into the last NTT pass as NVLink peer stores into CUDA-IPC mapped leaf blocks; sub-tree roots are all-gathered
-with NCCL and combined.  Prints one JSON line from rank 0.
+fused into the last NTT pass as NVLink peer stores into CUDA-IPC mapped leaf blocks; the "rows complete" barrier and the
+all-gather of the sub-tree roots run as one-warp kernels over peer mailboxes (torch.distributed only exchanges the IPC handles).  Prints one JSON line from rank 0.
 
   python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 tools/sharded_commit.py --log-n 23
 """
@@ -94,7 +94,8 @@ def main():
         print(json.dumps({"workload": f"sharded commit: {batch} polynomials of 2^{log_n} coefficients, rate 1/2, {rows} leaves x {w}",
                           "n_gpus": world, "same_device": args.same_device, "ms_per_commit": ms, "commits_per_s": 1e3 / ms,
                           "alg_gbs_ntt_plus_merkle": (nbytes_ntt + nbytes_mrk) / ms / 1e6,
-                          "exchange": "fused into the last NTT pass (peer stores via CUDA IPC) + all_gather of sub-roots over " + backend,
+                          "exchange": "fused into the last NTT pass (peer stores via CUDA IPC); stream barrier and all-gather of the sub-roots as "
+                                      "one-warp kernels over peer mailboxes (host collectives only at set-up, backend " + backend + ")",
                           "root_matches_single_gpu": ok, "opening_matches_single_gpu": open_ok, "open_ms": open_ms,
                           "root": [int(x) for x in root]}))
     if world > 1:
