@@ -359,7 +359,8 @@ def bench_sharded(pk, ctx, dist, rank: int, world: int, coll_device, log_n_commi
 
     def nvlink_tx_bytes():
         """NVLink payload bytes this rank's GPU has transmitted so far (NVML counters summed over its links, KiB
-        granularity; `nvidia-smi nvlink -gt d` as the fallback)."""
+        granularity).  None where the driver does not expose the counters (the B200 boxes of this pod do not: neither NVML nor
+        `nvidia-smi nvlink -gt d` returns them) — the peer-store cost is then evidenced by tools/peer_store_cost.py."""
         try:
             nv, h = nvml_handle()
             total, seen = 0, 0
@@ -373,21 +374,9 @@ def bench_sharded(pk, ctx, dist, rank: int, world: int, coll_device, log_n_commi
                     seen += 1
             if seen:
                 return total
+            nv_note.append("NVML exposes no NVLink throughput counters on this box")
         except Exception as e:  # counters are evidence, never a reason to lose the line
             nv_note.append(f"nvml: {type(e).__name__}: {e}")
-        try:
-            import re
-            import subprocess
-            import torch
-            pr = torch.cuda.get_device_properties(torch.cuda.current_device())
-            bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
-            o = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", bus], capture_output=True, text=True, timeout=20).stdout
-            vals = [int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", o)]
-            if vals:
-                return sum(vals) * 1024
-            nv_note.append("nvidia-smi nvlink -gt d: no Data Tx lines")
-        except Exception as e:
-            nv_note.append(f"nvidia-smi: {type(e).__name__}: {e}")
         return None
 
     def p2p_gbs():
@@ -402,10 +391,10 @@ def bench_sharded(pk, ctx, dist, rank: int, world: int, coll_device, log_n_commi
                 torch.cuda.synchronize()
                 barrier()
                 t0 = time.perf_counter()
-                if rank == 0:
-                    dist.send(buf, 1)
-                elif rank == 1:
-                    dist.recv(buf, 0)
+                ops = [dist.P2POp(dist.isend, buf, 1)] if rank == 0 else [dist.P2POp(dist.irecv, buf, 0)] if rank == 1 else []
+                if ops:
+                    for req in dist.batch_isend_irecv(ops):
+                        req.wait()
                 torch.cuda.synchronize()
                 dt = time.perf_counter() - t0
                 best = dt if best is None else min(best, dt)
