@@ -197,6 +197,25 @@ __device__ __forceinline__ uint32_t mad4(uint32_t* acc, uint32_t x0, uint32_t x2
         : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(b));
     return c;
 }
+// acc[0..7] += x0,x2,x4,x6 * b as one carry chain whose carry out lands in `top` (the limb above acc[7]) INSIDE the same
+// chain: one IADD3.X.  Returning the carry and adding it in C++ (`top += mad4(..)`) costs three instructions per use — ptxas
+// materialises the predicate as an increment, a predicated move and a pair-aligning move — i.e. 32 extra instructions per
+// Montgomery product.
+__device__ __forceinline__ void mad4_top(uint32_t* acc, uint32_t& top, uint32_t x0, uint32_t x2, uint32_t x4, uint32_t x6,
+                                         uint32_t b) {
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+          "+r"(acc[7]), "+r"(top)
+        : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(b));
+}
 // e0 += o[1] (carry c); o = (o >> 64) + x1,x3,x5,x7 * b + c   (one chain; top limbs start from zero)
 __device__ __forceinline__ void mad4_rshift(uint32_t& e0, uint32_t* o, uint32_t x1, uint32_t x3, uint32_t x5,
                                             uint32_t x7, uint32_t b) {
@@ -222,11 +241,11 @@ __device__ __forceinline__ void mont_row(uint32_t* e, uint32_t* o, const fr& a, 
         mul4(e, a.v[0], a.v[2], a.v[4], a.v[6], bi);
     } else {
         mad4_rshift(e[0], o, a.v[1], a.v[3], a.v[5], a.v[7], bi);
-        o[7] += mad4(e, a.v[0], a.v[2], a.v[4], a.v[6], bi);
+        mad4_top(e, o[7], a.v[0], a.v[2], a.v[4], a.v[6], bi);
     }
     uint32_t m = e[0] * PK_NP0;
     (void)mad4(o, PK_P1, PK_P3, PK_P5, PK_P7, m);  // limb 8 never overflows (p < 2^254)
-    o[7] += mad4(e, PK_P0, PK_P2, PK_P4, PK_P6, m);
+    mad4_top(e, o[7], PK_P0, PK_P2, PK_P4, PK_P6, m);
 }
 
 // a * b * 2^-256 mod p.  LAZY = false: inputs in [0, p) (Montgomery form or raw, see skyscraper.cuh), output in [0, p).
