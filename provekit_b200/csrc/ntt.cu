@@ -115,7 +115,11 @@ static __device__ __forceinline__ void ntt_step(uint4* tile, const fr* tw, const
     const int items = (1 << (P.S - G)) << NTT8_NCL;
     for (int item = threadIdx.x; item < items; item += blockDim.x) {
         const int k = item & (NTT8_NC - 1), grp = item >> NTT8_NCL;
+#ifdef PK_NTT_SWAP
         const int swap = grp & 1;
+#else
+        const int swap = 0;  // see tile_get: the un-swapping selects cost more than the two-way bank conflict they avoid
+#endif
         const int low = grp & ((1 << hb0) - 1);
         const int e0 = ((grp >> hb0) << (hb0 + G)) | low;
         fr x[R];
