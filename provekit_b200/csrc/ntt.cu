@@ -70,8 +70,10 @@ static __device__ __forceinline__ void tma_store_commit_and_wait() {
 static __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Shared-memory tile in NATURAL layout (TMA writes plain bytes): element e at byte 32 e, i.e. [point][column] with a 128-byte
-// row.  A quarter-warp (8 lanes) touches two rows with four columns each; the lanes of the odd row take the high 16 bytes
-// first, so the eight 128-bit accesses of one instruction hit 32 distinct banks.
+// row.  A quarter-warp (8 lanes) touches two rows with four columns each.  With swap = 1 the lanes of the odd row take the
+// high 16 bytes first, so the eight 128-bit accesses of one instruction hit 32 distinct banks — at the price of 16 selects per
+// element round trip to put the halves back in order.  The kernel is bound by its instruction count, not by shared-memory
+// cycles, so it runs with swap = 0 (two-way conflicts, no selects; -DPK_NTT_SWAP restores the conflict-free form for A/B).
 static __device__ __forceinline__ fr tile_get(const uint4* tile, int e, int swap) {
     const uint4* p = tile + 2 * e;
     const uint4 first = p[swap], second = p[swap ^ 1];
