@@ -644,7 +644,7 @@ int launch_multi_dot(cudaStream_t st, const void* const* a, int na, const void* 
     DotPtrs P = {};
     for (int i = 0; i < na; i++) P.a[i] = (const fr*)a[i];
     for (int i = 0; i < nb; i++) P.b[i] = (const fr*)b[i];
-    int g = grid_for(n, 256, REDUCE_MAX_BLOCKS);
+    int g = grid_for(n, 256, REDUCE_HEAVY_BLOCKS);
     if (na == 3 && nb == 2)
         k_multi_dot<3, 2><<<g, 256, 0, st>>>(P, n, (fr*)partials, (fr*)result);
     else if (na == 1 && nb == 2)
@@ -672,7 +672,7 @@ int launch_multi_tensor_dot(cudaStream_t st, const void* const* a, int na, size_
                             int lo_bits, void* partials, void* result) {
     DotPtrs P = {};
     for (int i = 0; i < na; i++) P.a[i] = (const fr*)a[i];
-    int g = grid_for(n, 256, REDUCE_MAX_BLOCKS);
+    int g = grid_for(n, 256, REDUCE_HEAVY_BLOCKS);
     if (na == 1)
         k_multi_tensor_dot<1><<<g, 256, 0, st>>>(P, n, (const fr*)hi, (const fr*)lo, lo_bits, (fr*)partials, (fr*)result);
     else if (na == 2)
@@ -825,7 +825,7 @@ int launch_zk_sumcheck_round(cudaStream_t st, void* a, void* b, void* c, void* e
                              fr_arg fold, const void* fold_ptr, void* partials, void* result) {
     size_t n_after = (size_t)1 << (has_fold ? log_n - 1 : log_n);
     size_t half = n_after / 2;
-    int g = grid_for(half, 256, REDUCE_MAX_BLOCKS);
+    int g = grid_for(half, 256, REDUCE_HEAVY_BLOCKS);
     if (has_fold)
         k_zk_sumcheck<true><<<g, 256, 0, st>>>((fr*)a, (fr*)b, (fr*)c, (fr*)eq, half, fold, (const fr*)fold_ptr, (fr*)partials,
                                                (fr*)result);
@@ -872,7 +872,7 @@ int launch_whir_sumcheck_round(cudaStream_t st, const void* p_in, const void* w_
                                int log_n, bool has_fold, fr_arg fold, const void* fold_ptr, void* partials, void* result) {
     size_t n_after = (size_t)1 << (has_fold ? log_n - 1 : log_n);
     size_t pairs = n_after / 2;
-    int g = grid_for(pairs, 256, REDUCE_MAX_BLOCKS);
+    int g = grid_for(pairs, 256, REDUCE_HEAVY_BLOCKS);
     if (has_fold)
         k_whir_sumcheck<true><<<g, 256, 0, st>>>((const fr*)p_in, (const fr*)w_in, (fr*)p_out, (fr*)w_out, pairs, fold,
                                                  (const fr*)fold_ptr, (fr*)partials, (fr*)result);

@@ -197,6 +197,13 @@ int launch_pow_grind(cudaStream_t st, PowCtrl* c, fr_arg threshold, int blocks);
 int launch_pow_end(cudaStream_t st, void* ts, PowCtrl* c);
 
 constexpr int REDUCE_MAX_BLOCKS = 1184;  // 148 SMs x 8
+// The multiplier-heavy reduction kernels (sumcheck rounds, batched dot products: 128 registers, two 256-thread blocks per SM)
+// launch ONE resident wave and loop: with 1184 blocks a thread of round 0 ran 1.7 iterations before a block reduction of
+// three 256-bit sums (5 shuffle levels of 8 SHFL + a field addition each, ~500 instructions) — 13-19 % of the kernel.
+#ifndef PK_HEAVY_REDUCE_BLOCKS
+#define PK_HEAVY_REDUCE_BLOCKS (148 * 2)
+#endif
+constexpr int REDUCE_HEAVY_BLOCKS = PK_HEAVY_REDUCE_BLOCKS;
 constexpr int REDUCE_MAX_SUMS = 6;       // field sums per reduction kernel
 // bytes of the partials work area: per-block partial sums + the ticket counter of the single-launch reduction
 constexpr size_t REDUCE_AREA_BYTES = (size_t)REDUCE_MAX_BLOCKS * REDUCE_MAX_SUMS * 32 + 64;
