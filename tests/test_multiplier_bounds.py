@@ -161,3 +161,55 @@ def test_lazy_butterfly_ranges():
             t = device_mul(d, w, lazy=True)  # the twiddle product of the butterfly
             assert t < 2 * P and t % P == (a - b) * w * R_INV % P
             assert normalize(s) == (a + b) % P and normalize(t) == (a - b) * w * R_INV % P
+
+
+# ---- the table-driven Feistel round of the hash (skyscraper.cuh: sky_round_sum<1|2>) ---------------------------------------
+def _parse_tables():
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "provekit_b200", "csrc", "skyscraper.cuh")).read()
+
+    def rows(block):
+        out = []
+        for r in re.findall(r"\{([^{}]*)\}", block):
+            w = [int(x.strip().rstrip("u"), 16) for x in r.split(",") if x.strip()]
+            if len(w) == 8:
+                out.append(sum(v << (32 * k) for k, v in enumerate(w)))
+        return out
+
+    rc = rows(re.search(r"SKY_RC\[18\]\[8\] = \{(.*?)\n\};", src, re.S).group(1))
+    rcq = rows(re.search(r"#define PK_RCQ_ROWS \\\n(.*?)\n\n", src, re.S).group(1))
+    qp = rows(re.search(r"SKY_QP\[6\]\[8\] = \{(.*?)\n\};", src, re.S).group(1))
+    return rc, rcq, qp
+
+
+def test_round_tables_hold_what_their_comments_say():
+    rc, rcq, qp = _parse_tables()
+    assert len(rc) == 18 and len(rcq) == 90 and len(qp) == 6
+    assert all(x < P for x in rc) and rc[0] == 0 and rc[17] == 0
+    for i in range(18):
+        for q in range(5):
+            assert rcq[5 * i + q] == (rc[i] - q * P) % R
+    assert qp == [q * P for q in range(6)]
+
+
+def test_table_round_keeps_the_lazy_range():
+    """state < B = 2p + 5 * 2^224 is a fixed point of: s0 = r + F; q = floor(s0[7] / (p[7] + 1)); s = s0 + (rc - q p) mod 2^256,
+    for F = a lazy square of a state (< x^2 / 2^256 + p) or a bar output (< p); q never exceeds the table (4) and nothing wraps."""
+    rc, rcq, _ = _parse_tables()
+    B = 2 * P + 5 * (1 << 224)
+    f_sqr_max = (B - 1) * (B - 1) // R + P  # (x^2 + m p) / 2^256 with m < 2^256
+    assert B - 1 + f_sqr_max < R  # r + F never wraps
+    top_p1 = (P >> 224) + 1
+    rng = random.Random(4)
+    samples = [(B - 1, f_sqr_max), (B - 1, 0), (0, f_sqr_max), (0, 0), (B - 1, P - 1), (P, P)]
+    samples += [(rng.randrange(B), rng.randrange(f_sqr_max + 1)) for _ in range(2000)]
+    for r_, f in samples:
+        s0 = r_ + f
+        q = (s0 >> 224) // top_p1
+        assert q <= 4
+        assert 0 <= s0 - q * P < P + 5 * (1 << 224)
+        for i in (0, 1, 5, 6, 11, 16, 17):
+            s = (s0 + rcq[5 * i + q]) % R
+            assert s == s0 - q * P + rc[i]  # the modular wrap of the table entry cancels exactly
+            assert s < B and s % P == (r_ + f + rc[i]) % P
