@@ -48,10 +48,19 @@ __device__ __forceinline__ uint32_t rotl_bytes(uint32_t v) {
     asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(d) : "r"(a), "r"(b), "r"(low));  // (a & ~low) | (b & low)
     return d;
 }
+#ifdef PK_BAR_SLOW
 __device__ __forceinline__ uint32_t sbox4(uint32_t v) {
     const uint32_t t1 = rotl_bytes<1>(v), t2 = rotl_bytes<2>(v), t3 = rotl_bytes<3>(v);
     return rotl_bytes<1>((~t1 & t2 & t3) ^ v);
 }
+#else
+// rotl2(v) & rotl3(v) = rotl2(v & rotl1(v)): three byte-wise rotations instead of four, 6 SHF + 5 LOP3 per word
+__device__ __forceinline__ uint32_t sbox4(uint32_t v) {
+    const uint32_t t1 = rotl_bytes<1>(v);
+    const uint32_t t23 = rotl_bytes<2>(v & t1);
+    return rotl_bytes<1>((~t1 & t23) ^ v);
+}
+#endif
 
 // q * p for q = 0..5 (skyscraper/core/src/constants.rs:9-16 MODULUS[0..5]) as 32-bit limbs
 __constant__ uint32_t SKY_QP[6][8] = {
@@ -64,6 +73,9 @@ __constant__ uint32_t SKY_QP[6][8] = {
 };
 // value < 2^256 -> [0, p): q = floor(top limb / (P7+1)) in 0..5, subtract q*p, one conditional subtract
 // (the reduce_partial idea of skyscraper/core/src/reduce.rs:33-40 followed by reduce_1 :21-29)
+// LAZY: stop after the subtraction of q p, i.e. return a representative in [0, p + 6 * 2^224) — enough for a bar output that
+// goes straight into a table-driven round sum (which only needs r + F < 5 p; see sky_round_sum)
+template <bool LAZY = false>
 __device__ __forceinline__ fr sky_reduce(const fr& x) {
     uint32_t q = x.v[7] / (PK_P7 + 1u);
     uint32_t qp[8];
@@ -83,15 +95,16 @@ __device__ __forceinline__ fr sky_reduce(const fr& x) {
           "=r"(d.v[7])
         : "r"(x.v[0]), "r"(x.v[1]), "r"(x.v[2]), "r"(x.v[3]), "r"(x.v[4]), "r"(x.v[5]), "r"(x.v[6]), "r"(x.v[7]),
           "r"(qp[0]), "r"(qp[1]), "r"(qp[2]), "r"(qp[3]), "r"(qp[4]), "r"(qp[5]), "r"(qp[6]), "r"(qp[7]));
-    return fr_reduce_once(d);
+    return LAZY ? d : fr_reduce_once(d);
 }
 
 // bar on a canonical value: swap the 16-byte halves, sbox every byte, reduce (reference.rs:80-94)
+template <bool LAZY = false>
 __device__ __forceinline__ fr sky_bar(const fr& x) {
     fr y;
     y.v[0] = sbox4(x.v[4]); y.v[1] = sbox4(x.v[5]); y.v[2] = sbox4(x.v[6]); y.v[3] = sbox4(x.v[7]);
     y.v[4] = sbox4(x.v[0]); y.v[5] = sbox4(x.v[1]); y.v[6] = sbox4(x.v[2]); y.v[7] = sbox4(x.v[3]);
-    return sky_reduce(y);
+    return sky_reduce<LAZY>(y);
 }
 
 __device__ __forceinline__ fr sky_rc(int i) {
@@ -321,8 +334,13 @@ __device__ __forceinline__ fr sky_compress_while(const fr& l_in, const fr& r_in,
         }
         const bool is_bar = (j == 3) | (j == 5);
         if (is_bar) {
-            r = sky_round_sum<MODE>(r, sky_bar(sky_canon(l)), 2 * j);
-            l = sky_round_sum<MODE>(l, sky_bar(sky_canon(r)), 2 * j + 1);
+#ifdef PK_BAR_SLOW
+            constexpr bool LAZY_BAR = false;
+#else
+            constexpr bool LAZY_BAR = MODE != 0;  // the table-driven sum absorbs a bar output below p + 6 * 2^224
+#endif
+            r = sky_round_sum<MODE>(r, sky_bar<LAZY_BAR>(sky_canon(l)), 2 * j);
+            l = sky_round_sum<MODE>(l, sky_bar<LAZY_BAR>(sky_canon(r)), 2 * j + 1);
         } else {
             r = sky_round_sum<MODE>(r, fr_sqr_lazy(l), 2 * j);
             l = sky_round_sum<MODE>(l, fr_sqr_lazy(r), 2 * j + 1);

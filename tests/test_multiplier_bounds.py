@@ -202,7 +202,12 @@ def test_table_round_keeps_the_lazy_range():
     assert B - 1 + f_sqr_max < R  # r + F never wraps
     top_p1 = (P >> 224) + 1
     rng = random.Random(4)
-    samples = [(B - 1, f_sqr_max), (B - 1, 0), (0, f_sqr_max), (0, 0), (B - 1, P - 1), (P, P)]
+    f_bar_max = P + 6 * (1 << 224) - 1  # a lazily reduced bar output: y - q p with q = floor(y[7] / (p[7] + 1)) <= 5
+    assert f_bar_max < f_sqr_max  # the squaring bound covers it
+    for y in (R - 1, 5 * P + 12345, 6 * (P >> 224 << 224), P, 0):  # sky_reduce<LAZY>: never negative, below the bound
+        qy = (y >> 224) // ((P >> 224) + 1)
+        assert qy <= 5 and 0 <= y - qy * P <= f_bar_max
+    samples = [(B - 1, f_sqr_max), (B - 1, 0), (0, f_sqr_max), (0, 0), (B - 1, P - 1), (P, P), (B - 1, f_bar_max)]
     samples += [(rng.randrange(B), rng.randrange(f_sqr_max + 1)) for _ in range(2000)]
     for r_, f in samples:
         s0 = r_ + f
